@@ -1,0 +1,130 @@
+"""Shared host logic of the five transforms: input checks, dtype and clip policy,
+and the call into the ``equilib_b200::remap`` op."""
+
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib, _ops
+
+Rot = Union[Dict[str, float], List[Dict[str, float]]]
+
+SUPPORTED = (torch.uint8, torch.float16, torch.bfloat16, torch.float32)
+
+
+def check_backend(kwargs: dict) -> None:
+    """The reference threads ``backend=`` ("native" | "pure") and ``cache=`` through
+    **kwargs (e.g. equilib/equi2pers/base.py:59-72,155).  Here the only backend is
+    the fused CUDA one; ``cache`` is accepted and ignored (tables are cached per
+    device in _prep)."""
+    backend = kwargs.pop("backend", None)
+    kwargs.pop("cache", None)
+    if backend not in (None, "b200"):
+        raise ValueError(
+            f"ERR: {backend} is not supported by equilib_b200 (only 'b200'); use the "
+            "reference package for the 'native' and 'pure' backends"
+        )
+
+
+def pop_options(kwargs: dict) -> Tuple[bool, bool]:
+    """Extensions over the reference API (both default to reference behaviour /
+    the documented policy): ``exact_clip`` and ``saturate_uint8``."""
+    exact_clip = bool(kwargs.pop("exact_clip", os.environ.get("EQUILIB_B200_EXACT_CLIP") == "1"))
+    saturate = bool(kwargs.pop("saturate_uint8", False))
+    if kwargs:
+        raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+    return exact_clip, saturate
+
+
+def require_cuda_tensor(x, name: str) -> None:
+    if isinstance(x, np.ndarray):
+        raise ValueError(
+            f"ERR: `{name}` is a numpy array; equilib_b200 accelerates CUDA torch tensors only "
+            "(use the reference's numpy path)"
+        )
+    if not torch.is_tensor(x):
+        raise ValueError(f"ERR: `{name}` is neither numpy nor torch")
+    if not x.is_cuda:
+        raise ValueError(
+            f"ERR: `{name}` is on {x.device}; equilib_b200 has no CPU path (move it to CUDA or "
+            "use the reference's torch-CPU path)"
+        )
+
+
+def check_image(img: torch.Tensor, name: str) -> torch.Tensor:
+    assert len(img.shape) == 4, (
+        f"ERR: input `{name}` should be 4-dim (b, c, h, w), but got {len(img.shape)}"
+    )
+    assert img.dtype in SUPPORTED + (torch.float64,), (
+        f"ERR: input {name} has dtype of {img.dtype} which is\n"
+        f"incompatible: try {SUPPORTED}"
+    )
+    if img.dtype == torch.float64:
+        raise NotImplementedError("float64 images are not implemented by equilib_b200")
+    if img.stride(3) != 1:
+        img = img.contiguous()
+    return img
+
+
+def normalise_single(img: torch.Tensor, rots: Rot):
+    """equilib/equi2pers/base.py:119-130 (same in every rotation-taking transform)."""
+    is_single = False
+    if len(img.shape) == 3 and isinstance(rots, dict):
+        img = img[None, ...]
+        rots = [rots]
+        is_single = True
+    elif len(img.shape) == 3:
+        img = img[:, None, ...]
+    assert isinstance(rots, list), "ERR: rots is not a list"
+    return img, rots, is_single
+
+
+def clip_tensor(src: torch.Tensor, mode: str, clip_output: bool, exact_clip: bool,
+                always: bool = False) -> Optional[torch.Tensor]:
+    """Device tensor {lo, hi} for ``torch.clip(out, torch.min(src), torch.max(src))``
+    (e.g. equilib/equi2equi/torch.py:195-198), or None when no clamp is launched.
+
+    uint8 and clip_output=False never clip (reference).  For float images the global
+    min/max pass is skipped where the clamp cannot change the stored result: nearest
+    (outputs are input values) and bilinear (a convex combination: fp32 rounding can
+    overshoot the maximum by at most 2 ulp, invisible after a 16-bit rounding; for
+    fp32 pass ``exact_clip=True`` to reproduce the reference's clamp exactly).
+    ``always`` is used by pers2equi, whose fill value depends on the clamp."""
+    if src.dtype == torch.uint8 or not clip_output:
+        return None
+    if not (always or exact_clip or mode == "bicubic"):
+        return None
+    out2 = torch.empty(2, dtype=torch.float32, device=src.device)
+    _ops.minmax(src, out2)
+    return out2
+
+
+def flags_of(dtype: torch.dtype, saturate_uint8: bool) -> int:
+    return _lib.FLAG_SATURATE_U8 if (saturate_uint8 and dtype == torch.uint8) else 0
+
+
+def mode_code(mode: str) -> int:
+    if mode not in _lib.MODES:
+        raise ValueError(f"ERR: {mode} is not supported")
+    return _lib.MODES[mode]
+
+
+def launch(src: torch.Tensor, out: torch.Tensor, *, transform: int, mode: str, flags: int,
+           batch: int, channels: int, src_hw: Tuple[int, int], dst_hw: Tuple[int, int],
+           src_strides: Sequence[int], dst_strides: Sequence[int], mats=None, tab_x=None,
+           tab_y=None, itab_x=None, grid=None, grid_stride_b: int = 0, clip=None,
+           w_face: int = 0, n_cells: int = 0, cell_offset: Optional[Sequence[int]] = None,
+           face_ptrs=None) -> None:
+    offs = list(cell_offset) if cell_offset is not None else []
+    offs = offs + [0] * (12 - len(offs))
+    _ops.remap(
+        src, out, mats, tab_x, tab_y, itab_x, grid, clip, face_ptrs,
+        transform, mode_code(mode), flags, batch, channels,
+        src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
+        [int(s) for s in src_strides], [int(s) for s in dst_strides],
+        int(grid_stride_b), w_face, n_cells, offs,
+    )

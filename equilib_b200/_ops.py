@@ -1,0 +1,156 @@
+"""torch custom ops over the C ABI: ``equilib_b200::remap``, ``::minmax``, ``::coords``.
+
+The ops only marshal pointers, sizes and strides into an ``eqb_remap_desc`` and
+launch on ``torch.cuda.current_stream()`` of the tensor's device.  They never
+allocate, never synchronise and have no CPU implementation.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_DTYPES = {
+    torch.uint8: _lib.U8,
+    torch.float16: _lib.F16,
+    torch.bfloat16: _lib.BF16,
+    torch.float32: _lib.F32,
+}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise NotImplementedError(
+            f"equilib_b200 supports uint8, float16, bfloat16 and float32 images, got {dt}"
+        ) from None
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.EquilibB200Error(
+            f"{name} must be a CUDA tensor: equilib_b200 has no CPU path (got {t.device})"
+        )
+
+
+def _f32_on(t: Optional[Tensor], dev: torch.device, name: str) -> None:
+    if t is None:
+        return
+    if t.device != dev or not t.is_contiguous():
+        raise _lib.EquilibB200Error(f"{name} must be contiguous and on {dev}")
+
+
+def _fill_desc(src, out, mats, tab_x, tab_y, itab_x, grid, clip, transform, mode, flags, batch,
+               channels, src_h, src_w, dst_h, dst_w, src_strides, dst_strides, grid_stride_b,
+               w_face, n_cells, cell_offset, face_ptrs) -> _lib.RemapDesc:
+    d = _lib.RemapDesc()
+    d.transform, d.mode, d.flags = transform, mode, flags
+    d.batch, d.channels = batch, channels
+    d.src_h, d.src_w, d.dst_h, d.dst_w = src_h, src_w, dst_h, dst_w
+    if src is not None:
+        d.dtype = dtype_code(src.dtype)
+        d.src = src.data_ptr()
+        d.src_stride_b, d.src_stride_c, d.src_stride_h = src_strides
+    if out is not None:
+        d.dst = out.data_ptr()
+        d.dst_stride_b, d.dst_stride_c, d.dst_stride_h = dst_strides
+    d.mats, d.tab_x, d.tab_y = _ptr(mats), _ptr(tab_x), _ptr(tab_y)
+    d.itab_x, d.grid, d.clip = _ptr(itab_x), _ptr(grid), _ptr(clip)
+    d.grid_stride_b = grid_stride_b
+    d.w_face, d.n_cells = w_face, n_cells
+    for i, v in enumerate(cell_offset):
+        d.cell_offset[i] = v
+    d.face_ptrs = _ptr(face_ptrs)
+    return d
+
+
+@torch.library.custom_op("equilib_b200::remap", mutates_args=("out",), device_types="cuda")
+def remap(
+    src: Tensor,
+    out: Tensor,
+    mats: Optional[Tensor],
+    tab_x: Optional[Tensor],
+    tab_y: Optional[Tensor],
+    itab_x: Optional[Tensor],
+    grid: Optional[Tensor],
+    clip: Optional[Tensor],
+    face_ptrs: Optional[Tensor],
+    transform: int,
+    mode: int,
+    flags: int,
+    batch: int,
+    channels: int,
+    src_h: int,
+    src_w: int,
+    dst_h: int,
+    dst_w: int,
+    src_strides: List[int],
+    dst_strides: List[int],
+    grid_stride_b: int,
+    w_face: int,
+    n_cells: int,
+    cell_offset: List[int],
+) -> None:
+    """One fused remap launch (eqb_remap).  ``out`` is written in place."""
+    _require_cuda(src, "src")
+    _require_cuda(out, "out")
+    dev = src.device
+    if out.device != dev or out.dtype != src.dtype:
+        raise _lib.EquilibB200Error("src and out must share device and dtype")
+    for t, n in ((mats, "mats"), (tab_x, "tab_x"), (tab_y, "tab_y"), (itab_x, "itab_x"),
+                 (grid, "grid"), (clip, "clip"), (face_ptrs, "face_ptrs")):
+        _f32_on(t, dev, n)
+    d = _fill_desc(src, out, mats, tab_x, tab_y, itab_x, grid, clip, transform, mode, flags,
+                   batch, channels, src_h, src_w, dst_h, dst_w, src_strides, dst_strides,
+                   grid_stride_b, w_face, n_cells, cell_offset, face_ptrs)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().eqb_remap(C.byref(d), C.c_void_p(stream)), "eqb_remap")
+
+
+@torch.library.custom_op("equilib_b200::minmax", mutates_args=("out2",), device_types="cuda")
+def minmax(img: Tensor, out2: Tensor) -> None:
+    """Global min/max of a (B, C, H, W) image batch into a 2-float device tensor."""
+    _require_cuda(img, "img")
+    if img.dim() != 4 or img.stride(3) != 1:
+        raise _lib.EquilibB200Error("minmax expects a 4-d tensor with unit inner stride")
+    if out2.device != img.device or out2.dtype != torch.float32 or out2.numel() != 2:
+        raise _lib.EquilibB200Error("out2 must be 2 float32 values on the image's device")
+    im = _lib.Image()
+    im.data = img.data_ptr()
+    im.dtype = dtype_code(img.dtype)
+    im.batch, im.channels, im.height, im.width = img.shape
+    im.stride_b, im.stride_c, im.stride_h = img.stride(0), img.stride(1), img.stride(2)
+    with torch.cuda.device(img.device):
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        _lib.check(
+            _lib.lib().eqb_minmax(C.byref(im), C.c_void_p(out2.data_ptr()), C.c_void_p(stream)),
+            "eqb_minmax",
+        )
+
+
+def coords(coords_out: Tensor, mats, tab_x, tab_y, itab_x, grid, transform: int, batch: int,
+           src_h: int, src_w: int, dst_h: int, dst_w: int, grid_stride_b: int = 0, w_face: int = 0,
+           n_cells: int = 0) -> None:
+    """eqb_remap_coords: the transform's sampling grid (B, 2, dst_h, dst_w), for tests."""
+    _require_cuda(coords_out, "coords_out")
+    d = _fill_desc(None, None, mats, tab_x, tab_y, itab_x, grid, None, transform, 0, 0, batch, 1,
+                   src_h, src_w, dst_h, dst_w, (0, 0, 0), (0, 0, 0), grid_stride_b, w_face,
+                   n_cells, [0] * 12, None)
+    with torch.cuda.device(coords_out.device):
+        stream = torch.cuda.current_stream(coords_out.device).cuda_stream
+        _lib.check(
+            _lib.lib().eqb_remap_coords(C.byref(d), C.c_void_p(coords_out.data_ptr()),
+                                        C.c_void_p(stream)),
+            "eqb_remap_coords",
+        )

@@ -1,0 +1,320 @@
+// extern "C" boundary of libequilib_b200.so (see include/equilib_b200.h).
+// Validates descriptors, picks the store width, launches.  No allocation, no sync.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "remap_kernels.cuh"
+
+namespace eqb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static size_t elt_size(int dtype) {
+  switch (dtype) {
+    case EQB_U8: return 1;
+    case EQB_F16:
+    case EQB_BF16: return 2;
+    case EQB_F32: return 4;
+  }
+  return 0;
+}
+
+static int vec_px(int dtype, int mode) { return (dtype == EQB_U8 && mode != EQB_BICUBIC) ? 4 : 2; }
+
+// Common validation + Params fill.  `need_images` is false for eqb_remap_coords.
+static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
+  if (!d) return fail(EQB_ERR_INVALID, "null descriptor");
+  if (d->transform < EQB_EQUI2EQUI || d->transform > EQB_GRID)
+    return fail(EQB_ERR_INVALID, "unknown transform %d", d->transform);
+  if (d->batch <= 0 || d->batch > 65535)
+    return fail(EQB_ERR_INVALID, "batch %d out of range [1, 65535]", d->batch);
+  if (d->dst_h <= 0 || d->dst_w <= 0 || d->src_h < 2 || d->src_w < 2)
+    return fail(EQB_ERR_INVALID, "bad sizes: src %dx%d (each must be >= 2), dst %dx%d", d->src_h,
+                d->src_w, d->dst_h, d->dst_w);
+  if ((d->dst_h + kTileH - 1) / kTileH > 65535)
+    return fail(EQB_ERR_INVALID, "dst_h %d too large", d->dst_h);
+  std::memset(&p, 0, sizeof(p));
+  p.B = d->batch;
+  p.C = d->channels;
+  p.sh = d->src_h;
+  p.sw = d->src_w;
+  p.dh = d->dst_h;
+  p.dw = d->dst_w;
+  p.mats = d->mats;
+  p.tx = d->tab_x;
+  p.ty = d->tab_y;
+  p.itx = d->itab_x;
+  p.grid = d->grid;
+  p.gsb = d->grid_stride_b;
+  p.clip = d->clip;
+  p.inv_wm1 = 1.0f / (float)(d->src_w - 1);
+  p.inv_hm1 = 1.0f / (float)(d->src_h - 1);
+  p.w_face = d->w_face;
+  p.n_cells = d->n_cells;
+  p.flags = d->flags;
+  p.face_ptrs = d->face_ptrs;
+  for (int i = 0; i < 12; ++i) p.cell_off[i] = d->cell_offset[i];
+
+  const int xf = d->transform;
+  if (xf != EQB_CUBE2EQUI && xf != EQB_GRID && !d->mats)
+    return fail(EQB_ERR_INVALID, "mats is required for transform %d", xf);
+  if ((xf == EQB_EQUI2EQUI || xf == EQB_PERS2EQUI) && (!d->tab_x || !d->tab_y))
+    return fail(EQB_ERR_INVALID, "tab_x/tab_y are required for transform %d", xf);
+  if (xf == EQB_EQUI2CUBE) {
+    if (!d->tab_x) return fail(EQB_ERR_INVALID, "tab_x (rng) is required for equi2cube");
+    if (d->w_face <= 0 || (d->n_cells != 6 && d->n_cells != 12))
+      return fail(EQB_ERR_INVALID, "equi2cube needs w_face > 0 and n_cells in {6, 12}");
+    if (d->dst_h != d->w_face || d->dst_w != d->n_cells * d->w_face)
+      return fail(EQB_ERR_INVALID, "equi2cube canvas must be w_face x n_cells*w_face");
+  }
+  if (xf == EQB_CUBE2EQUI) {
+    if (!d->tab_x || !d->tab_y || !d->itab_x)
+      return fail(EQB_ERR_INVALID, "tab_x/tab_y/itab_x are required for cube2equi");
+    if (d->w_face < 2 || d->src_h != d->w_face || d->src_w != 6 * d->w_face)
+      return fail(EQB_ERR_INVALID, "cube2equi source must be the w_face x 6*w_face strip");
+  }
+  if (xf == EQB_GRID && !d->grid) return fail(EQB_ERR_INVALID, "grid is required for EQB_GRID");
+
+  if (need_images) {
+    if (d->mode < EQB_NEAREST || d->mode > EQB_BICUBIC)
+      return fail(EQB_ERR_INVALID, "unknown mode %d", d->mode);
+    if (!elt_size(d->dtype)) return fail(EQB_ERR_INVALID, "unknown dtype %d", d->dtype);
+    if (d->channels <= 0) return fail(EQB_ERR_INVALID, "channels must be positive");
+    if (!d->dst) return fail(EQB_ERR_INVALID, "dst is null");
+    if (!d->src && !(xf == EQB_CUBE2EQUI && d->face_ptrs))
+      return fail(EQB_ERR_INVALID, "src is null");
+    if (d->src_stride_h < (xf == EQB_CUBE2EQUI ? d->w_face : d->src_w))
+      return fail(EQB_ERR_INVALID, "src_stride_h smaller than a row");
+    {
+      // in-plane source offsets are 32-bit in the kernels
+      long long span = (long long)d->src_stride_h * d->src_h;
+      if (xf == EQB_CUBE2EQUI && !d->face_ptrs)
+        for (int i = 0; i < 6; ++i)
+          if (d->cell_offset[i] + span > span) span = d->cell_offset[i] + span;
+      if (span >= (1ll << 31))
+        return fail(EQB_ERR_UNSUPPORTED, "a source plane spans %lld elements (limit 2^31)", span);
+    }
+    p.src = d->src;
+    p.dst = d->dst;
+    p.ssb = d->src_stride_b;
+    p.ssc = d->src_stride_c;
+    p.ssh = d->src_stride_h;
+    p.dsb = d->dst_stride_b;
+    p.dsc = d->dst_stride_c;
+    p.dsh = d->dst_stride_h;
+  }
+  return EQB_OK;
+}
+
+// Widest store the destination layout allows: every row start of every plane (and
+// cell) must be aligned to PX elements.
+static int pick_px(const eqb_remap_desc* d) {
+  const int v = vec_px(d->dtype, d->mode);
+  const size_t bytes = v * elt_size(d->dtype);
+  if (reinterpret_cast<uintptr_t>(d->dst) % bytes) return 1;
+  if (d->dst_stride_b % v || d->dst_stride_c % v || d->dst_stride_h % v) return 1;
+  if (d->transform == EQB_EQUI2CUBE) {
+    if (d->w_face % v) return 1;
+    for (int i = 0; i < d->n_cells; ++i)
+      if (d->cell_offset[i] % v) return 1;
+  }
+  return v;
+}
+
+template <int XF> static cudaError_t go(const Params& p, const eqb_remap_desc* d, int px,
+                                        cudaStream_t s) {
+  return launch_remap<XF>(p, d->mode, d->dtype, px, s);
+}
+
+// ---------------------------------------------------------------------------
+// min / max reduction (clip_output)
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned enc(float f) {  // order-preserving float -> uint
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec(unsigned e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+__global__ void minmax_init(unsigned* out) {
+  out[0] = 0xffffffffu;
+  out[1] = 0u;
+}
+__global__ void minmax_fini(unsigned* out) {
+  const float lo = dec(out[0]), hi = dec(out[1]);
+  reinterpret_cast<float*>(out)[0] = lo;
+  reinterpret_cast<float*>(out)[1] = hi;
+}
+
+// One row-segment per thread iteration; rows are contiguous, so consecutive threads
+// read consecutive elements.  Grid-stride over (plane-row, x-chunk).
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ data, int B, int C,
+                                                     int H, int W, long long sb, long long sc,
+                                                     long long sh, unsigned* out) {
+  float lo = INFINITY, hi = -INFINITY;
+  const long long rows = (long long)B * C * H;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int y = (int)(r % H);
+    const long long bc = r / H;
+    const int c = (int)(bc % C);
+    const long long b = bc / C;
+    const T* row = data + b * sb + c * sc + y * sh;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+      const float v = ld_f(row + x);
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[8], shi[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { slo[warp] = lo; shi[warp] = hi; }
+  __syncthreads();
+  if (warp == 0) {
+    lo = lane < 8 ? slo[lane] : INFINITY;
+    hi = lane < 8 ? shi[lane] : -INFINITY;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) {
+      atomicMin(out, enc(lo));
+      atomicMax(out + 1, enc(hi));
+    }
+  }
+}
+
+}  // namespace eqb
+
+using namespace eqb;
+
+extern "C" {
+
+int32_t eqb_abi_version(void) { return EQB_ABI_VERSION; }
+
+const char* eqb_last_error(void) { return g_err; }
+
+int64_t eqb_launch_count(void) { return g_launches.load(); }
+
+int32_t eqb_remap(const eqb_remap_desc* d, void* stream) {
+  Params p;
+  const int rc = fill(d, true, p);
+  if (rc != EQB_OK) return rc;
+  const int px = pick_px(d);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  switch (d->transform) {
+    case EQB_EQUI2EQUI: e = go<EQB_EQUI2EQUI>(p, d, px, s); break;
+    case EQB_EQUI2PERS: e = go<EQB_EQUI2PERS>(p, d, px, s); break;
+    case EQB_EQUI2CUBE: e = go<EQB_EQUI2CUBE>(p, d, px, s); break;
+    case EQB_CUBE2EQUI: e = go<EQB_CUBE2EQUI>(p, d, px, s); break;
+    case EQB_PERS2EQUI: e = go<EQB_PERS2EQUI>(p, d, px, s); break;
+    default: e = go<EQB_GRID>(p, d, px, s); break;
+  }
+  if (e != cudaSuccess)
+    return fail(EQB_ERR_CUDA, "remap launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  g_err[0] = 0;
+  return EQB_OK;
+}
+
+int32_t eqb_remap_coords(const eqb_remap_desc* d, float* coords_out, void* stream) {
+  Params p;
+  const int rc = fill(d, false, p);
+  if (rc != EQB_OK) return rc;
+  if (!coords_out) return fail(EQB_ERR_INVALID, "coords_out is null");
+  p.coords_out = coords_out;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  switch (d->transform) {
+    case EQB_EQUI2EQUI: e = launch_coords<EQB_EQUI2EQUI>(p, s); break;
+    case EQB_EQUI2PERS: e = launch_coords<EQB_EQUI2PERS>(p, s); break;
+    case EQB_EQUI2CUBE: e = launch_coords<EQB_EQUI2CUBE>(p, s); break;
+    case EQB_CUBE2EQUI: e = launch_coords<EQB_CUBE2EQUI>(p, s); break;
+    case EQB_PERS2EQUI: e = launch_coords<EQB_PERS2EQUI>(p, s); break;
+    default: e = launch_coords<EQB_GRID>(p, s); break;
+  }
+  if (e != cudaSuccess)
+    return fail(EQB_ERR_CUDA, "coords launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  g_err[0] = 0;
+  return EQB_OK;
+}
+
+int32_t eqb_minmax(const eqb_image* im, float* out2, void* stream) {
+  if (!im || !im->data || !out2) return fail(EQB_ERR_INVALID, "null argument");
+  if (im->batch <= 0 || im->channels <= 0 || im->height <= 0 || im->width <= 0)
+    return fail(EQB_ERR_INVALID, "empty image");
+  if (!elt_size(im->dtype)) return fail(EQB_ERR_INVALID, "unknown dtype %d", im->dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned* o = reinterpret_cast<unsigned*>(out2);
+  const long long rows = (long long)im->batch * im->channels * im->height;
+  const int blocks = (int)(rows < 148 * 16 ? rows : 148 * 16);
+  minmax_init<<<1, 1, 0, s>>>(o);
+#define EQB_MM(T)                                                                          \
+  minmax_kernel<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(im->data), im->batch,     \
+                                          im->channels, im->height, im->width,            \
+                                          im->stride_b, im->stride_c, im->stride_h, o)
+  switch (im->dtype) {
+    case EQB_U8: EQB_MM(uint8_t); break;
+    case EQB_F16: EQB_MM(__half); break;
+    case EQB_BF16: EQB_MM(__nv_bfloat16); break;
+    default: EQB_MM(float); break;
+  }
+#undef EQB_MM
+  minmax_fini<<<1, 1, 0, s>>>(o);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(EQB_ERR_CUDA, "minmax launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(3);
+  g_err[0] = 0;
+  return EQB_OK;
+}
+
+int32_t eqb_rotation_compose(const float* trig, int32_t n, float* out) {
+  if (!trig || !out || n < 0) return fail(EQB_ERR_INVALID, "null argument");
+  // C = A @ B for 3x3 fp32 as the FMA chain k = 0, 1, 2 that torch's 2-D mm
+  // produces for equilib/torch_utils/rotation.py:77 (SURVEY probe B15).
+  auto mm = [](const float* A, const float* B, float* C) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float acc = A[i * 3 + 0] * B[0 * 3 + j];
+        acc = fmaf(A[i * 3 + 1], B[1 * 3 + j], acc);
+        acc = fmaf(A[i * 3 + 2], B[2 * 3 + j], acc);
+        C[i * 3 + j] = acc;
+      }
+  };
+  for (int k = 0; k < n; ++k) {
+    const float* t = trig + (size_t)k * 6;
+    const float cr = t[0], sr = t[1], cp = t[2], sp = t[3], cy = t[4], sy = t[5];
+    const float Rx[9] = {1.f, 0.f, 0.f, 0.f, cr, -sr, 0.f, sr, cr};
+    const float Ry[9] = {cp, 0.f, sp, 0.f, 1.f, 0.f, -sp, 0.f, cp};
+    const float Rz[9] = {cy, -sy, 0.f, sy, cy, 0.f, 0.f, 0.f, 1.f};
+    float T[9];
+    mm(Rz, Ry, T);
+    mm(T, Rx, out + (size_t)k * 9);
+  }
+  return EQB_OK;
+}
+
+}  // extern "C"

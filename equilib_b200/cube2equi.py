@@ -1,0 +1,198 @@
+"""Cube2Equi / cube2equi -- drop-in for equilib/cube2equi/base.py:34-160 (CUDA).
+
+The reference first copies every cube format into a horizon strip
+(equilib/cube2equi/torch.py:15-132) and samples that strip, so bilinear/bicubic
+taps bleed across face boundaries in F,R,B,L,U,D order.  Here the kernel reads the
+faces where they are ("horizon" and "dice" tensors in place, "list"/"dict" faces
+through a device table of face pointers) and reproduces the strip's cross-face
+bleed arithmetically.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Union
+
+import numpy as np
+import torch
+
+from . import _common as K
+from . import _lib, _ops, _prep
+from .equi2cube import DICE_CELLS, FACE_KEYS
+
+__all__ = ["Cube2Equi", "cube2equi"]
+
+
+class Cube2Equi(object):
+    """
+    params:
+    - height, width (int): equirectangular image size
+    - cube_format (str): input cube format ("dice", "horizon", "dict", "list")
+    - clip_output (bool), mode (str)
+    """
+
+    def __init__(
+        self,
+        height: int,
+        width: int,
+        cube_format: str,
+        clip_output: bool = True,
+        mode: str = "bilinear",
+    ) -> None:
+        self.height = height
+        self.width = width
+        self.cube_format = cube_format
+        self.clip_output = clip_output
+        self.mode = mode
+
+    def __call__(self, cubemap, **kwargs) -> torch.Tensor:
+        return cube2equi(
+            cubemap=cubemap,
+            cube_format=self.cube_format,
+            width=self.width,
+            height=self.height,
+            clip_output=self.clip_output,
+            mode=self.mode,
+            **kwargs,
+        )
+
+
+def _first_leaf(cubemap, cube_format: str):
+    """The tensor used for type sniffing, equilib/cube2equi/base.py:96-128."""
+    if cube_format in ("dice", "horizon"):
+        return cubemap
+    if cube_format == "dict":
+        if isinstance(cubemap, dict):
+            return cubemap["F"]
+        assert isinstance(cubemap, list) and isinstance(cubemap[0], dict)
+        return cubemap[0]["F"]
+    if cube_format == "list":
+        assert isinstance(cubemap, list)
+        return cubemap[0][0] if isinstance(cubemap[0], list) else cubemap[0]
+    raise ValueError(f"ERR: {cube_format} is not supported")
+
+
+def _face_lists(cubemap, cube_format: str) -> List[List[torch.Tensor]]:
+    """list / dict formats -> [[F, R, B, L, U, D] per batch item]."""
+    if cube_format == "list":
+        if isinstance(cubemap[0], torch.Tensor):
+            cubemap = [cubemap]
+        return [list(cube) for cube in cubemap]
+    if isinstance(cubemap, dict):
+        cubemap = [cubemap]
+    assert isinstance(cubemap[0], dict), (
+        f"ERR: cubemap {cube_format} needs to have dict inside the list"
+    )
+    return [[cube[k] for k in FACE_KEYS] for cube in cubemap]
+
+
+def cube2equi(
+    cubemap,
+    cube_format: str,
+    height: int,
+    width: int,
+    clip_output: bool = True,
+    mode: str = "bilinear",
+    **kwargs,
+) -> torch.Tensor:
+    assert width % 8 == 0 and height % 8 == 0
+    leaf = _first_leaf(cubemap, cube_format)
+    assert leaf is not None and (isinstance(leaf, np.ndarray) or torch.is_tensor(leaf)), (
+        "ERR: input type is not numpy or torch"
+    )
+    K.require_cuda_tensor(leaf, "cubemap")
+    K.check_backend(kwargs)
+    exact_clip, saturate = K.pop_options(kwargs)
+    out = run(cubemap, cube_format, height=height, width=width, mode=mode,
+              clip_output=clip_output, exact_clip=exact_clip, saturate_uint8=saturate)
+    if out.shape[0] == 1:
+        out = out.squeeze(0)
+    return out
+
+
+def _minmax_views(views, device) -> torch.Tensor:
+    parts = []
+    for v in views:
+        o = torch.empty(2, dtype=torch.float32, device=device)
+        _ops.minmax(v, o)
+        parts.append(o)
+    if len(parts) == 1:
+        return parts[0]
+    st = torch.stack(parts)
+    return torch.stack([st[:, 0].min(), st[:, 1].max()])
+
+
+def run(cubemap, cube_format, height, width, mode, clip_output=True, exact_clip=False,
+        saturate_uint8=False) -> torch.Tensor:
+    """Replaces convert2horizon + equilib/cube2equi/torch.py:248-357."""
+    K.mode_code(mode)
+    face_ptrs = None
+    if cube_format in ("horizon", "dice"):
+        assert isinstance(cubemap, torch.Tensor), (
+            f"ERR: cubemap {cube_format} needs to be a torch.Tensor"
+        )
+        cm = cubemap
+        if cm.dim() == 2:
+            cm = cm[None, None, ...]
+        elif cm.dim() == 3:
+            cm = cm[None, ...]
+        assert cm.dim() == 4, f"ERR: cubemap needs to be 4 dim, but got {cm.shape}"
+        cm = K.check_image(cm, "cubemap")
+        bs, c = cm.shape[:2]
+        if cube_format == "horizon":
+            w = cm.shape[-2]
+            assert cm.shape[-1] == 6 * w
+            cells = [f * w for f in range(6)]
+            clip_views = [cm]
+        else:
+            w = cm.shape[-2] // 3
+            assert cm.shape[-2] == w * 3 and cm.shape[-1] == w * 4
+            cells = [sy * w * cm.stride(2) + sx * w for sx, sy in DICE_CELLS]
+            clip_views = [cm[:, :, w:2 * w, :], cm[:, :, 0:w, w:2 * w],
+                          cm[:, :, 2 * w:3 * w, w:2 * w]]
+        src = cm
+        src_strides = cm.stride()[:3]
+    elif cube_format in ("list", "dict"):
+        faces = _face_lists(cubemap, cube_format)
+        f0 = faces[0][0]
+        assert f0.dim() == 3
+        c, w, _ = f0.shape
+        bs = len(faces)
+        flat = [f for cube in faces for f in cube]
+        assert all(f.shape == f0.shape and f.dtype == f0.dtype and f.device == f0.device
+                   for f in flat), "ERR: cube faces differ in shape, dtype or device"
+        K.check_image(f0[None], "cubemap")
+        need_clip = (f0.dtype != torch.uint8 and clip_output
+                     and (exact_clip or mode == "bicubic"))
+        same_layout = all(f.stride() == f0.stride() for f in flat) and f0.stride(2) == 1
+        if same_layout and not need_clip:
+            # zero-copy: a device table of B x 6 face base pointers
+            ptrs = torch.tensor([f.data_ptr() for f in flat], dtype=torch.int64)
+            face_ptrs = ptrs.to(f0.device, non_blocking=True)
+            src = f0
+            src_strides = (0, f0.stride(0), f0.stride(1))
+            cells = [0] * 6
+            clip_views = []
+            _keepalive = flat  # noqa: F841  (faces outlive the launch via the caller)
+        else:
+            src = torch.stack([torch.stack(cube) for cube in faces])  # (B, 6, C, w, w)
+            src_strides = (src.stride(0), src.stride(2), src.stride(3))
+            cells = [f * src.stride(1) for f in range(6)]
+            clip_views = [src.view(bs, 6 * c, w, w)]
+    else:
+        raise ValueError(f"ERR: {cube_format} is not supported")
+
+    dev = src.device
+    tab_x, tab_y, itab_x = _prep.cube2equi_tables(height, width, dev)
+    clip = None
+    if src.dtype != torch.uint8 and clip_output and (exact_clip or mode == "bicubic"):
+        clip = _minmax_views(clip_views, dev)
+    out = torch.empty((bs, c, height, width), dtype=src.dtype, device=dev)
+    K.launch(
+        src, out, transform=_lib.CUBE2EQUI, mode=mode,
+        flags=K.flags_of(src.dtype, saturate_uint8), batch=bs, channels=c,
+        src_hw=(w, 6 * w), dst_hw=(height, width),
+        src_strides=src_strides, dst_strides=out.stride()[:3],
+        tab_x=tab_x, tab_y=tab_y, itab_x=itab_x, clip=clip,
+        w_face=w, n_cells=6, cell_offset=cells, face_ptrs=face_ptrs,
+    )
+    return out

@@ -1,0 +1,101 @@
+"""Equi2Pers / equi2pers -- drop-in for equilib/equi2pers/base.py:19-164 (CUDA)."""
+
+from __future__ import annotations
+
+from typing import Dict, List, Union
+
+import torch
+
+from . import _common as K
+from . import _lib, _prep
+
+__all__ = ["Equi2Pers", "equi2pers"]
+
+Rot = Union[Dict[str, float], List[Dict[str, float]]]
+
+
+class Equi2Pers(object):
+    """
+    params:
+    - height, width (int): perspective size
+    - fov_x (float): perspective image fov of x-axis (degrees)
+    - skew (float), z_down (bool), mode (str), clip_output (bool)
+    """
+
+    def __init__(
+        self,
+        height: int,
+        width: int,
+        fov_x: float,
+        skew: float = 0.0,
+        z_down: bool = False,
+        mode: str = "bilinear",
+        clip_output: bool = True,
+    ) -> None:
+        self.height = height
+        self.width = width
+        self.fov_x = fov_x
+        self.skew = skew
+        self.mode = mode
+        self.z_down = z_down
+        self.clip_output = clip_output
+
+    def __call__(self, equi: torch.Tensor, rots: Rot, **kwargs) -> torch.Tensor:
+        return equi2pers(
+            equi=equi,
+            rots=rots,
+            height=self.height,
+            width=self.width,
+            fov_x=self.fov_x,
+            skew=self.skew,
+            z_down=self.z_down,
+            mode=self.mode,
+            clip_output=self.clip_output,
+            **kwargs,
+        )
+
+
+def equi2pers(
+    equi: torch.Tensor,
+    rots: Rot,
+    height: int,
+    width: int,
+    fov_x: float,
+    skew: float = 0.0,
+    mode: str = "bilinear",
+    z_down: bool = False,
+    clip_output: bool = True,
+    **kwargs,
+) -> torch.Tensor:
+    K.require_cuda_tensor(equi, "equi")
+    K.check_backend(kwargs)
+    exact_clip, saturate = K.pop_options(kwargs)
+    equi, rots, is_single = K.normalise_single(equi, rots)
+    out = run(equi, rots, height=height, width=width, fov_x=fov_x, skew=skew, z_down=z_down,
+              mode=mode, clip_output=clip_output, exact_clip=exact_clip, saturate_uint8=saturate)
+    if is_single:
+        out = out.squeeze(0)
+    return out
+
+
+def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
+        exact_clip=False, saturate_uint8=False) -> torch.Tensor:
+    """Replaces equilib/equi2pers/torch.py:96-244 with one fused launch."""
+    equi = K.check_image(equi, "equi")
+    assert len(equi) == len(rots), (
+        f"ERR: length of equi and rot differs: {len(equi)} vs {len(rots)}"
+    )
+    K.mode_code(mode)
+    bs, c, h_equi, w_equi = equi.shape
+    dev = equi.device
+    mats = _prep.mats_for("equi2pers", rots, z_down, dev,
+                          (int(height), int(width), float(fov_x), float(skew)))
+    clip = K.clip_tensor(equi, mode, clip_output, exact_clip)
+    out = torch.empty((bs, c, height, width), dtype=equi.dtype, device=dev)
+    K.launch(
+        equi, out, transform=_lib.EQUI2PERS, mode=mode,
+        flags=K.flags_of(equi.dtype, saturate_uint8), batch=bs, channels=c,
+        src_hw=(h_equi, w_equi), dst_hw=(height, width),
+        src_strides=equi.stride()[:3], dst_strides=out.stride()[:3], mats=mats, clip=clip,
+    )
+    return out

@@ -1,0 +1,167 @@
+/*
+ * equilib_b200 -- C ABI of the B200 (sm_100a) remap kernels.
+ *
+ * Drop-in boundary for equilib's torch remap path.  Every entry point is
+ * `extern "C"`, takes plain pointers/sizes (no torch types), never allocates
+ * device memory, never synchronises and never throws: it returns an
+ * `eqb_status` and records a thread-local message readable with
+ * `eqb_last_error()`.  All device pointers must belong to the CUDA device that
+ * is current on the calling thread; `stream` is a `cudaStream_t` passed as
+ * `void*` (NULL = legacy default stream).
+ *
+ * Reference interfaces replaced (paths in haruishi43/equilib v0.6.0):
+ *   eqb_remap            <- the torch `run()` bodies: grid prep + matmul +
+ *                           convert_grid + torch_grid_sample + clip, i.e.
+ *                           equilib/equi2equi/torch.py:143-198,
+ *                           equilib/equi2pers/torch.py:186-243,
+ *                           equilib/equi2cube/torch.py:189-251,
+ *                           equilib/cube2equi/torch.py:324-357,
+ *                           equilib/pers2equi/torch.py:196-253
+ *                           (no H x W x 2 grid is ever materialised);
+ *                           with transform = EQB_GRID it replaces
+ *                           equilib/grid_sample/torch/native.py:11-90
+ *                           (`native()` -> F.grid_sample) for a caller-made grid.
+ *   eqb_remap_coords     <- `convert_grid` of each transform, e.g.
+ *                           equilib/equi2equi/torch.py:24-42 (test/debug aid).
+ *   eqb_minmax           <- `torch.min(src)`, `torch.max(src)` feeding
+ *                           `torch.clip`, e.g. equilib/equi2equi/torch.py:197.
+ *   eqb_rotation_compose <- `R_z @ R_y @ R_x` of
+ *                           equilib/torch_utils/rotation.py:27-78 (host code).
+ */
+#ifndef EQUILIB_B200_H_
+#define EQUILIB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQB_ABI_VERSION 1
+
+typedef enum eqb_status {
+  EQB_OK = 0,
+  EQB_ERR_INVALID = -1,     /* bad descriptor (null pointer, size, enum value) */
+  EQB_ERR_UNSUPPORTED = -2, /* valid request the library does not implement   */
+  EQB_ERR_CUDA = -3         /* a CUDA runtime call failed                     */
+} eqb_status;
+
+typedef enum eqb_transform {
+  EQB_EQUI2EQUI = 0,
+  EQB_EQUI2PERS = 1,
+  EQB_EQUI2CUBE = 2,
+  EQB_CUBE2EQUI = 3,
+  EQB_PERS2EQUI = 4,
+  EQB_GRID = 5 /* sample with a caller-supplied pixel-unit (y, x) grid */
+} eqb_transform;
+
+typedef enum eqb_mode { EQB_NEAREST = 0, EQB_BILINEAR = 1, EQB_BICUBIC = 2 } eqb_mode;
+
+typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eqb_dtype;
+
+/* flags */
+#define EQB_FLAG_SATURATE_U8 1u /* uint8 store saturates instead of wrapping mod 256 */
+#define EQB_FLAG_NORM_DIV 2u    /* normalise with a true division (reference CPU     \
+                                   flavour) instead of a reciprocal multiply (CUDA)  */
+
+/*
+ * One remap launch.  Images are planar NCHW views with unit inner stride;
+ * strides are in ELEMENTS.  A zero batch stride (expanded batch) is allowed for
+ * the source.
+ *
+ * Per transform:
+ *   EQUI2EQUI  src = equirect (src_h x src_w), dst = equirect (dst_h x dst_w).
+ *              mats = B x 9 (R).  tab_x = [cos(theta) | sin(theta)] (2*dst_w),
+ *              tab_y = [cos(phi) | sin(phi)] (2*dst_h).
+ *   EQUI2PERS  src = equirect, dst = perspective.  mats = B x 9 (R @ G).
+ *   EQUI2CUBE  src = equirect, dst = cube canvas.  mats = B x 9 (R).
+ *              tab_x = rng (w_face).  dst_h = w_face, dst_w = n_cells * w_face:
+ *              the canvas is n_cells (6 or 12) square cells side by side; cell i
+ *              lives at element offset cell_offset[i] inside a (b, c) plane of
+ *              dst with row stride dst_stride_h; cells 0..5 are faces
+ *              F,R,B,L,U,D, cells 6..11 (dice background) are zero-filled.
+ *   CUBE2EQUI  src = cube, dst = equirect.  src_h = w_face, src_w = 6 * w_face
+ *              (the virtual horizon strip the reference samples from); face i
+ *              lives at cell_offset[i] inside a (b, c) plane of src with row
+ *              stride src_stride_h.  If face_ptrs != NULL it is a device array
+ *              of B x 6 base pointers (one C x w x w face each, addressed with
+ *              src_stride_c / src_stride_h) and src / cell_offset are ignored.
+ *              tab_x = [tanx | cosx | sin(theta) | cos(theta)] (4*dst_w),
+ *              tab_y = [ntan | cu | cd] (3*dst_h), itab_x = [face | thr] (2*dst_w).
+ *   PERS2EQUI  src = perspective, dst = equirect.  mats = B x 9 (G @ R);
+ *              tables as EQUI2EQUI.
+ *   GRID       grid = B x 2 x dst_h x dst_w fp32, (y, x) source pixel units,
+ *              batch stride grid_stride_b (0 = shared by all batch items).
+ */
+typedef struct eqb_remap_desc {
+  int32_t transform; /* eqb_transform */
+  int32_t mode;      /* eqb_mode      */
+  int32_t dtype;     /* eqb_dtype of src and dst */
+  uint32_t flags;
+
+  int32_t batch;
+  int32_t channels;
+  int32_t src_h, src_w;
+  int32_t dst_h, dst_w;
+
+  const void* src;
+  int64_t src_stride_b, src_stride_c, src_stride_h;
+  void* dst;
+  int64_t dst_stride_b, dst_stride_c, dst_stride_h;
+
+  const float* mats;     /* device, batch x 9, row-major */
+  const float* tab_x;    /* device, per output column    */
+  const float* tab_y;    /* device, per output row       */
+  const int32_t* itab_x; /* device, per output column    */
+  const float* grid;     /* device, EQB_GRID only        */
+  int64_t grid_stride_b;
+  const float* clip;     /* device float[2] {lo, hi}, or NULL for no clip */
+
+  int32_t w_face;
+  int32_t n_cells;
+  int64_t cell_offset[12];
+  const void* const* face_ptrs;
+} eqb_remap_desc;
+
+/* Plain planar image view, for eqb_minmax. */
+typedef struct eqb_image {
+  const void* data;
+  int32_t dtype;
+  int32_t batch, channels, height, width;
+  int64_t stride_b, stride_c, stride_h;
+} eqb_image;
+
+/* ABI version of the loaded library (== EQB_ABI_VERSION it was built with). */
+int32_t eqb_abi_version(void);
+
+/* Message of the last failing call on this thread ("" if none). */
+const char* eqb_last_error(void);
+
+/* Fused ray generation + ray-to-pixel map + sampling + output policy. */
+int32_t eqb_remap(const eqb_remap_desc* desc, void* stream);
+
+/*
+ * Writes the sampling coordinates of the transform (what the reference calls
+ * the grid: B x 2 x dst_h x dst_w fp32, (uj, ui) in source pixel units, before
+ * the sampler's normalisation) to `coords_out`.  src/dst/dtype are ignored.
+ * For tests and debugging; not used by the product path.
+ */
+int32_t eqb_remap_coords(const eqb_remap_desc* desc, float* coords_out, void* stream);
+
+/* Global min and max of an image batch -> out2[0], out2[1] (device floats). */
+int32_t eqb_minmax(const eqb_image* img, float* out2, void* stream);
+
+/*
+ * HOST function.  trig = n x 6 floats (cos r, sin r, cos p, sin p, cos y, sin y;
+ * the caller applies the z_down sign flip and the float64 -> float32 rounding);
+ * out = n x 9 floats, R = (R_z @ R_y) @ R_x with fp32 fused multiply-add chains.
+ */
+int32_t eqb_rotation_compose(const float* trig, int32_t n, float* out);
+
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t eqb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQUILIB_B200_H_ */

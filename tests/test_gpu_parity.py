@@ -1,0 +1,446 @@
+"""GPU parity tests: the CUDA path (through the public API -> torch custom op ->
+C ABI) against the CPU oracle and against the committed reference outputs.
+
+Tolerances (stated once, used below):
+* coordinates: |d| <= 1e-6 * size px.  Every fp32 step of the chain is mirrored
+  exactly except asinf/atan2f, which differ from the host libm by a few ulp of an
+  angle of magnitude <= pi, i.e. <= ~1e-6 rad = 1.6e-7 * size px.
+* fp32 bilinear/bicubic on the band-limited parity image:
+  rtol 1e-5, atol 1e-5 (BASELINE.json north_star), >= 99.9 % of pixels.
+* fp32 on uniform-noise images (worst case, |grad| ~ 1 / px): the same coordinate
+  noise becomes <= size * 1e-6 in value; bound 5e-4 absolute.
+* nearest: identical except where a coordinate sits within the noise of a .5 tie:
+  >= 99.5 % identical pixels.
+* uint8: identical code values except truncation flips: |d| <= 1, >= 99 % identical
+  (bicubic overshoot wraps exactly like the reference, compared modulo 256).
+* fp16 / bf16: oracle = fp32 math on the up-cast input rounded once; 1 ulp of the
+  output type (2^-10 / 2^-7 relative).
+"""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import equilib_b200
+import oracle
+from equilib_b200 import _lib, _ops, _prep
+from oracle import remap_oracle as O
+from tests import cases, helpers
+
+pytestmark = pytest.mark.gpu
+
+DEV = torch.device("cuda", 0)
+GOLD = helpers.load_golden()
+GOLDEN_CASES = [c for c in cases.golden_cases()]
+MODES = ("nearest", "bilinear", "bicubic")
+
+
+def product_run(case, img, kw):
+    t = case["transform"]
+    kw = dict(kw)
+    fn = getattr(equilib_b200, t)
+    x = torch.from_numpy(img).to(DEV)
+    if t == "cube2equi":
+        return fn(x, **kw)
+    rots = kw.pop("rots")
+    return fn(x, rots, **kw)
+
+
+def compare(case, out, ref):
+    out = cases.to_numpy(out)
+    ref = cases.to_numpy(ref)
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    assert out.dtype == ref.dtype
+    if case["dtype"] == "uint8":
+        d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+        d = np.minimum(d, 256 - d)
+        assert d.max() <= 1, d.max()
+        assert np.mean(d == 0) >= 0.99
+    elif case["mode"] == "nearest":
+        assert np.mean(out == ref) >= 0.995
+    else:
+        assert np.abs(out - ref).max() <= 5e-4, np.abs(out - ref).max()
+        assert helpers.frac_close(out, ref, rtol=1e-5, atol=2e-5) >= 0.99
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c["name"] for c in GOLDEN_CASES])
+def test_golden_case_vs_oracle_and_reference(case):
+    img, kw = cases.build_inputs(case)
+    out = product_run(case, img, kw)
+    torch.cuda.synchronize()
+    if case["dtype"] == "float16":
+        ref = helpers.oracle_run(case, img.astype(np.float32), kw, flavour="cuda")
+        o = cases.to_numpy(out)
+        assert out.dtype == torch.float16
+        assert np.abs(o - ref.numpy()).max() <= 2 ** -10 + 5e-4
+        return
+    ref = helpers.oracle_run(case, img, kw, flavour="cuda")
+    compare(case, out, ref)
+    # the committed outputs of the unmodified reference (CPU flavour: differs from
+    # the CUDA flavour by one rounding in the normalisation step)
+    compare(case, out, GOLD[case["name"] + "/out"])
+
+
+# ---------------------------------------------------------------------------
+# coordinate-level parity through eqb_remap_coords
+# ---------------------------------------------------------------------------
+
+
+def circ_diff(a, b, period):
+    d = np.abs(a - b)
+    return np.minimum(d, np.abs(period - d))
+
+
+def gpu_coords(transform, rots, z_down, dst_hw, src_hw, extra=None, w_face=0):
+    b = len(rots) if rots else 1
+    dh, dw = dst_hw
+    mats = tab_x = tab_y = itab_x = None
+    if transform == _lib.EQUI2EQUI:
+        mats = _prep.mats_for("rot", rots, z_down, DEV)
+        tab_x, tab_y = _prep.equirect_tables(dh, dw, DEV)
+    elif transform == _lib.EQUI2PERS:
+        mats = _prep.mats_for("equi2pers", rots, z_down, DEV, extra)
+    elif transform == _lib.PERS2EQUI:
+        mats = _prep.mats_for("pers2equi", rots, z_down, DEV, extra)
+        tab_x, tab_y = _prep.equirect_tables(dh, dw, DEV)
+    elif transform == _lib.EQUI2CUBE:
+        mats = _prep.mats_for("rot", rots, not z_down, DEV)
+        tab_x = _prep.cube_rng_table(w_face, DEV)
+    elif transform == _lib.CUBE2EQUI:
+        tab_x, tab_y, itab_x = _prep.cube2equi_tables(dh, dw, DEV)
+    out = torch.empty((b, 2, dh, dw), dtype=torch.float32, device=DEV)
+    _ops.coords(out, mats, tab_x, tab_y, itab_x, None, transform, b, src_hw[0], src_hw[1], dh, dw,
+                w_face=w_face, n_cells=6 if transform == _lib.EQUI2CUBE else 0)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("z_down", [False, True])
+def test_coords_equi2equi(z_down):
+    rots = cases.rotation_sweep(6)
+    h, w = 256, 512
+    g = gpu_coords(_lib.EQUI2EQUI, rots, z_down, (h, w), (h, w))
+    uj, ui = O.equi2equi_coords(rots, z_down, h, w, h, w)
+    duj = np.abs(g[:, 0] - uj.numpy())
+    dui = circ_diff(g[:, 1], ui.numpy(), w)
+    print(f"equi2equi coords: max duj {duj.max():.2e} dui {dui.max():.2e} "
+          f"mean {duj.mean():.2e}/{dui.mean():.2e} exact {np.mean(duj == 0):.3f}/{np.mean(dui == 0):.3f}")
+    assert duj.max() <= 1e-6 * h * 4 and dui.max() <= 1e-6 * w * 4
+    assert duj.mean() <= 1e-6 * h and dui.mean() <= 1e-6 * w
+
+
+def test_coords_equi2pers():
+    rots = cases.rotation_sweep(5)
+    g = gpu_coords(_lib.EQUI2PERS, rots, False, (120, 160), (256, 512), extra=(120, 160, 90.0, 0.0))
+    uj, ui = O.equi2pers_coords(rots, False, 120, 160, 90.0, 0.0, 256, 512)
+    assert np.abs(g[:, 0] - uj.numpy()).max() <= 4e-6 * 256
+    assert circ_diff(g[:, 1], ui.numpy(), 512).max() <= 4e-6 * 512
+
+
+def test_coords_equi2cube():
+    rots = cases.rotation_sweep(5)
+    g = gpu_coords(_lib.EQUI2CUBE, rots, False, (64, 384), (256, 512), w_face=64)
+    uj, ui = O.equi2cube_coords(rots, False, 64, 256, 512)
+    assert np.abs(g[:, 0] - uj.numpy()).max() <= 4e-6 * 256
+    assert circ_diff(g[:, 1], ui.numpy(), 512).max() <= 4e-6 * 512
+
+
+def test_coords_cube2equi_bit_exact():
+    # no transcendental on the device: tables come from the host, the rest is
+    # mirrored arithmetic -> identical bits
+    g = gpu_coords(_lib.CUBE2EQUI, None, False, (128, 256), (64, 384), w_face=64)
+    uj, ui = O.cube2equi_coords(128, 256, 64)
+    assert np.array_equal(g[0, 0], uj[0].numpy())
+    assert np.array_equal(g[0, 1], ui[0].numpy())
+
+
+def test_coords_pers2equi_bit_exact():
+    rots = cases.rotation_sweep(5)
+    g = gpu_coords(_lib.PERS2EQUI, rots, False, (128, 256), (96, 128), extra=(96, 128, 90.0, 0.0))
+    uj, ui = O.pers2equi_coords(rots, False, 128, 256, 96, 128, 90.0, 0.0)
+    assert np.array_equal(g[:, 0], uj.numpy())
+    assert np.array_equal(g[:, 1], ui.numpy())
+
+
+# ---------------------------------------------------------------------------
+# sampler-only parity: same coordinates in, so only the sampler differs
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_grid_sample_matches_oracle_sampler(mode):
+    rng = np.random.default_rng(5)
+    img = rng.random((2, 3, 40, 56), dtype=np.float32)
+    # includes the seam, the poles, out-of-range and exact-integer coordinates
+    uj = rng.uniform(-1.5, 41.0, size=(2, 33, 47)).astype(np.float32)
+    ui = rng.uniform(-1.5, 57.5, size=(2, 33, 47)).astype(np.float32)
+    uj[:, 0, :8] = np.arange(8, dtype=np.float32)
+    ui[:, 0, :8] = 55.0
+    grid = np.stack([uj, ui], axis=1)
+    out = equilib_b200.grid_sample(torch.from_numpy(img).to(DEV), torch.from_numpy(grid).to(DEV),
+                                   mode=mode)
+    ref = O.sample(torch.from_numpy(img), torch.from_numpy(uj), torch.from_numpy(ui), mode, "cuda")
+    o, r = out.cpu().numpy(), ref.numpy()
+    if mode == "bicubic":
+        assert np.abs(o - r).max() <= 2e-6
+    else:
+        assert np.array_equal(o, r)
+
+
+# ---------------------------------------------------------------------------
+# the north-star tolerance on the band-limited parity image, realistic size
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+def test_equi2equi_fp32_band_limited_1e5(mode):
+    img = cases.band_limited_image((2, 3, 512, 1024), "float32")
+    rots = cases.bench_rotations(5)[3:]
+    out = equilib_b200.equi2equi(torch.from_numpy(img).to(DEV), rots, mode=mode)
+    ref = oracle.equi2equi(torch.from_numpy(img), rots, mode=mode, flavour="cuda")
+    frac = helpers.frac_close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+    print(f"equi2equi {mode} band-limited: frac within 1e-5 = {frac:.6f}, "
+          f"max abs {np.abs(out.cpu().numpy() - ref.numpy()).max():.2e}")
+    assert frac >= 0.999
+
+
+def test_equi2pers_fp32_band_limited_1e5():
+    img = cases.band_limited_image((1, 3, 512, 1024), "float32")
+    rot = {"roll": 0.1, "pitch": 0.3, "yaw": -0.5}
+    out = equilib_b200.equi2pers(torch.from_numpy(img[0]).to(DEV), rot, 240, 320, 90.0)
+    ref = oracle.equi2pers(torch.from_numpy(img[0]), rot, 240, 320, 90.0)
+    assert out.shape == (3, 240, 320)
+    assert helpers.frac_close(out.cpu().numpy(), ref.numpy(), 1e-5, 1e-5) >= 0.999
+
+
+# ---------------------------------------------------------------------------
+# dtypes
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("dtype,ulp", [(torch.float16, 2.0 ** -10), (torch.bfloat16, 2.0 ** -7)])
+@pytest.mark.parametrize("mode", MODES)
+def test_16bit_inputs(dtype, ulp, mode):
+    img = torch.from_numpy(cases.band_limited_image((2, 3, 128, 256), "float32", px=96, py=64))
+    img = img.to(dtype)
+    rots = cases.rotation_sweep(5)[3:]
+    out = equilib_b200.equi2equi(img.to(DEV), rots, mode=mode)
+    assert out.dtype == dtype
+    ref = oracle.equi2equi(img, rots, mode=mode, flavour="cuda")
+    assert ref.dtype == dtype
+    o, r = out.float().cpu().numpy(), ref.float().numpy()
+    if mode == "nearest":
+        assert np.mean(o == r) >= 0.995
+    else:
+        assert np.abs(o - r).max() <= ulp * 1.01 + 2e-4
+        assert np.mean(o == r) >= 0.98
+
+
+@pytest.mark.parametrize("odd", [False, True])
+def test_unaligned_output_rows_take_the_scalar_store_path(odd):
+    # odd widths / offset views break the vector-store alignment rules
+    w_out = 37 if odd else 40
+    img = cases.noise_image((2, 3, 32, 64), "uint8", 3)
+    rots = cases.rotation_sweep(5)[3:]
+    out = equilib_b200.equi2pers(torch.from_numpy(img).to(DEV), rots, 21, w_out, 80.0)
+    ref = oracle.equi2pers(torch.from_numpy(img), rots, 21, w_out, 80.0)
+    d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
+    assert d.max() <= 1 and np.mean(d == 0) >= 0.99
+
+
+def test_strided_and_expanded_sources():
+    base = torch.from_numpy(cases.noise_image((1, 3, 32, 64), "float32", 11)).to(DEV)
+    rots = cases.rotation_sweep(7)[3:]
+    expanded = base.expand(4, -1, -1, -1)  # stride-0 batch: one equirect, many views
+    a = equilib_b200.equi2pers(expanded, rots, 24, 32, 90.0)
+    b = equilib_b200.equi2pers(base.repeat(4, 1, 1, 1), rots, 24, 32, 90.0)
+    assert torch.equal(a, b)
+    wide = torch.zeros((4, 3, 40, 80), device=DEV)
+    wide[:, :, 4:36, 8:72] = base
+    c = equilib_b200.equi2pers(wide[:, :, 4:36, 8:72], rots, 24, 32, 90.0)
+    assert torch.equal(a, c)
+
+
+def test_class_api_is_bitwise_equal_to_func_api():
+    # tests/test_cache_consistency.py:88-118 of the reference
+    img = torch.from_numpy(cases.noise_image((2, 3, 32, 64), "float32", 42)).to(DEV)
+    for rots in (cases.rotation_sweep(5)[3:], cases.rotation_sweep(9)[7:]):
+        e2p = equilib_b200.Equi2Pers(24, 32, 90.0)
+        for _ in range(2):
+            assert torch.equal(e2p(img, rots), equilib_b200.equi2pers(img, rots, 24, 32, 90.0))
+        e2e = equilib_b200.Equi2Equi()
+        assert torch.equal(e2e(img, rots), equilib_b200.equi2equi(img, rots))
+        e2c = equilib_b200.Equi2Cube(16, "dice")
+        assert torch.equal(e2c(img, rots), equilib_b200.equi2cube(img, rots, 16, "dice"))
+        p2e = equilib_b200.Pers2Equi(32, 64)
+        assert torch.equal(p2e(img, rots, 90.0), equilib_b200.pers2equi(img, rots, 32, 64, 90.0))
+
+
+def test_equi2equi_class_ignores_ctor_size_like_the_reference():
+    img = torch.zeros((3, 64, 128), device=DEV)
+    out = equilib_b200.Equi2Equi(height=32, width=64)(img, {"roll": 0.0, "pitch": 0.0, "yaw": 0.0})
+    assert out.shape == (3, 64, 128)
+
+
+# ---------------------------------------------------------------------------
+# cube formats
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_equi2cube_formats_agree(mode):
+    img_np = cases.noise_image((2, 3, 32, 64), "float32", 21)
+    img = torch.from_numpy(img_np).to(DEV)
+    rots = cases.rotation_sweep(5)[3:]
+    hz = equilib_b200.equi2cube(img, rots, 16, "horizon", mode=mode)
+    dice = equilib_b200.equi2cube(img, rots, 16, "dice", mode=mode)
+    lst = equilib_b200.equi2cube(img, rots, 16, "list", mode=mode)
+    dct = equilib_b200.equi2cube(img, rots, 16, "dict", mode=mode)
+    ref_dice = oracle.equi2cube(torch.from_numpy(img_np), rots, 16, "dice", mode=mode)
+    assert dice.shape == (2, 3, 48, 64)
+    assert torch.equal(O.format_to_horizon(dice.cpu(), "dice"), hz.cpu())
+    assert torch.equal((dice.cpu() == 0) | (ref_dice != 0), torch.ones_like(ref_dice, dtype=bool))
+    for b in range(2):
+        for f, k in enumerate("FRBLUD"):
+            face = hz[b, :, :, f * 16:(f + 1) * 16]
+            assert torch.equal(lst[b][f], face)
+            assert torch.equal(dct[b][k], face)
+    single = equilib_b200.equi2cube(img[0], rots[0], 16, "dict", mode=mode)
+    assert isinstance(single, dict) and torch.equal(single["F"], dct[0]["F"])
+    with pytest.raises(NotImplementedError):
+        equilib_b200.equi2cube(img, rots, 16, "cross")
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("dtype", ["float32", "uint8"])
+def test_cube2equi_formats_agree(mode, dtype):
+    hz_np = cases.noise_image((2, 3, 16, 96), dtype, 31)
+    hz = torch.from_numpy(hz_np).to(DEV)
+    ref = oracle.cube2equi(torch.from_numpy(hz_np), "horizon", 32, 64, mode=mode)
+    out = equilib_b200.cube2equi(hz, "horizon", 32, 64, mode=mode)
+    case = dict(dtype=dtype, mode=mode)
+    compare(case, out, ref)
+    dice = O.horizon_to_format(torch.from_numpy(hz_np), "dice").to(DEV)
+    assert torch.equal(equilib_b200.cube2equi(dice, "dice", 32, 64, mode=mode), out)
+    lst = [[hz[b, :, :, f * 16:(f + 1) * 16].contiguous() for f in range(6)] for b in range(2)]
+    assert torch.equal(equilib_b200.cube2equi(lst, "list", 32, 64, mode=mode), out)
+    dct = [{k: lst[b][f] for f, k in enumerate("FRBLUD")} for b in range(2)]
+    assert torch.equal(equilib_b200.cube2equi(dct, "dict", 32, 64, mode=mode), out)
+    # non-contiguous faces (views of the strip) take the stacking path
+    views = [[hz[b, :, :, f * 16:(f + 1) * 16] for f in range(6)] for b in range(2)]
+    assert torch.equal(equilib_b200.cube2equi(views, "list", 32, 64, mode=mode), out)
+    one = equilib_b200.cube2equi(dct[0], "dict", 32, 64, mode=mode)
+    assert one.shape == (3, 32, 64) and torch.equal(one, out[0])
+
+
+# ---------------------------------------------------------------------------
+# size-independent properties at full (BASELINE.json) sizes
+# ---------------------------------------------------------------------------
+
+
+def test_full_size_nearest_only_moves_pixels():
+    """4K nearest: every output value is one of the input's values at the oracle's
+    rounded coordinate; checked through a checksum of per-row checksums on an image
+    whose pixel value encodes its own position."""
+    h, w = 2048, 4096
+    ys = torch.arange(h, dtype=torch.float32, device=DEV)[:, None]
+    xs = torch.arange(w, dtype=torch.float32, device=DEV)[None, :]
+    img = torch.stack([ys.expand(h, w), xs.expand(h, w)])[None]  # value == own (y, x)
+    rots = [{"roll": 0.3, "pitch": -0.4, "yaw": 1.1}]
+    out = equilib_b200.equi2equi(img, rots, mode="nearest")
+    coords = gpu_coords(_lib.EQUI2EQUI, rots, False, (h, w), (h, w))
+    uj = torch.from_numpy(coords[:, 0]).to(DEV)
+    ui = torch.from_numpy(coords[:, 1]).to(DEV)
+    # the sampler may only pick one of the <= 4 integer neighbours of (uj, ui)
+    assert float((out[0, 0] - uj[0]).abs().max()) <= 1.0 + 1e-3
+    dx = (out[0, 1] - ui[0]).abs()
+    dx = torch.minimum(dx, (w - dx).abs())
+    assert float(dx.max()) <= 1.0 + 1e-3
+    assert float(out[0, 0].min()) >= 0 and float(out[0, 0].max()) <= h - 1
+
+
+def test_full_size_linearity_and_constant_image():
+    """bilinear is linear in the image: f(2x) == 2 f(x) bit-for-bit (power of two),
+    and a constant image stays constant up to 2 ulp (weights sum to 1 +- rounding)."""
+    img = torch.from_numpy(cases.band_limited_image((1, 3, 2048, 4096), "float32")).to(DEV)
+    rots = [{"roll": 0.2, "pitch": 0.5, "yaw": -2.0}]
+    a = equilib_b200.equi2equi(img, rots, clip_output=False)
+    b = equilib_b200.equi2equi(img * 2, rots, clip_output=False)
+    assert torch.equal(a * 2, b)
+    const = torch.full((1, 1, 2048, 4096), 0.75, device=DEV)
+    c = equilib_b200.equi2equi(const, rots, clip_output=False)
+    assert float((c - 0.75).abs().max()) <= 2.5 * 2 ** -24
+    d = equilib_b200.equi2equi(const, rots, clip_output=True, exact_clip=True)
+    assert float(d.max()) == 0.75  # the reference's clamp removes the overshoot
+
+
+def test_full_size_cube_round_trip_psnr():
+    """equi -> cube (w=1024) -> equi at 4K: smooth image survives (no reference test
+    pins this)."""
+    img = torch.from_numpy(cases.band_limited_image((1, 3, 2048, 4096), "float32")).to(DEV)
+    rot = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}]
+    for fmt in ("dice", "horizon", "dict"):
+        cube = equilib_b200.equi2cube(img, rot, 1024, fmt, mode="bilinear")
+        back = equilib_b200.cube2equi(cube, fmt, 2048, 4096, mode="bilinear")
+        back = back if back.dim() == 4 else back[None]
+        mse = float(((back[:, :, 64:-64] - img[:, :, 64:-64]) ** 2).mean())
+        psnr = 10 * math.log10(1.0 / max(mse, 1e-20))
+        print(f"round trip {fmt}: PSNR {psnr:.1f} dB")
+        assert psnr > 35.0
+
+
+def test_pers2equi_fill_follows_clip_order():
+    pers = (torch.rand(1, 3, 96, 128, device=DEV) + 0.5)
+    rots = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}]
+    a = equilib_b200.pers2equi(pers, rots, 128, 256, 90.0, clip_output=True)
+    b = equilib_b200.pers2equi(pers, rots, 128, 256, 90.0, clip_output=False)
+    assert float((b == 0).float().mean()) > 0.5
+    assert torch.all(a[b == 0] == pers.min())
+
+
+def test_uint8_bicubic_wraps_like_the_reference_and_can_saturate():
+    img = np.zeros((1, 1, 32, 64), np.uint8)
+    img[..., 32:] = 255  # step edge -> bicubic overshoot
+    rot = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.3}]
+    x = torch.from_numpy(img).to(DEV)
+    wrap = equilib_b200.equi2equi(x, rot, mode="bicubic")
+    ref = oracle.equi2equi(torch.from_numpy(img), rot, mode="bicubic")
+    d = np.abs(wrap.cpu().numpy().astype(int) - ref.numpy().astype(int))
+    d = np.minimum(d, 256 - d)
+    assert d.max() <= 1
+    sat = equilib_b200.equi2equi(x, rot, mode="bicubic", saturate_uint8=True)
+    ref_sat = oracle.equi2equi(torch.from_numpy(img), rot, mode="bicubic", saturate_uint8=True)
+    assert np.abs(sat.cpu().numpy().astype(int) - ref_sat.numpy().astype(int)).max() <= 1
+    assert int(sat.max()) == 255 and int(sat.min()) == 0
+
+
+def test_errors_raise_before_launch():
+    img = torch.zeros((2, 3, 16, 32), device=DEV)
+    rots = cases.rotation_sweep(5)[3:]
+    n0 = _lib.launch_count()
+    with pytest.raises(AssertionError):
+        equilib_b200.equi2equi(img, rots[:1])
+    with pytest.raises(ValueError):
+        equilib_b200.equi2equi(img, rots, mode="lanczos")
+    with pytest.raises(ValueError):
+        equilib_b200.equi2equi(img, rots, backend="pure")
+    with pytest.raises(NotImplementedError):
+        equilib_b200.equi2equi(img.double(), rots)
+    with pytest.raises(TypeError):
+        equilib_b200.equi2equi(img, rots, bogus=1)
+    assert _lib.launch_count() == n0
+
+
+def test_launches_are_counted_and_on_current_stream():
+    img = torch.rand((1, 3, 64, 128), device=DEV)
+    rots = [{"roll": 0.0, "pitch": 0.1, "yaw": 0.2}]
+    s = torch.cuda.Stream()
+    n0 = _lib.launch_count()
+    with torch.cuda.stream(s):
+        a = equilib_b200.equi2equi(img, rots)
+    s.synchronize()
+    assert _lib.launch_count() == n0 + 1
+    b = equilib_b200.equi2equi(img, rots)
+    assert torch.equal(a, b)

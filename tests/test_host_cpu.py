@@ -1,0 +1,145 @@
+"""CPU-only checks of the host side: the C ABI loads and exports what the header
+declares, host prep (rotation matrices, tables, A matrices) equals the oracle, and
+the public API rejects what it must before any launch."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import equilib_b200
+from equilib_b200 import _lib, _prep
+from oracle import remap_oracle as O
+from tests import cases, helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPU = torch.device("cpu")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "equilib_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(eqb_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), (declared, set(_lib.EXPORTS))
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert _lib.lib().eqb_abi_version() == _lib.ABI_VERSION
+    assert _lib.lib().eqb_last_error() == b""
+
+
+def test_descriptor_validation_without_gpu():
+    d = _lib.RemapDesc()
+    L = _lib.lib()
+    assert L.eqb_remap(ctypes.byref(d), None) == -1
+    assert b"batch" in L.eqb_last_error()
+    assert L.eqb_remap(None, None) == -1
+    d.transform = 99
+    assert L.eqb_remap(ctypes.byref(d), None) == -1
+    assert b"transform" in L.eqb_last_error()
+
+
+def test_struct_layout_matches_header():
+    # sizeof(eqb_remap_desc): 10 int32 + 2x(ptr + 3 int64) + 5 ptr + int64 + ptr
+    #                         + 2 int32 + 12 int64 + ptr
+    assert ctypes.sizeof(_lib.RemapDesc) == 40 + 2 * 32 + 4 * 8 + 8 + 8 + 8 + 8 + 96 + 8
+    assert ctypes.sizeof(_lib.Image) == 8 + 5 * 4 + 4 + 3 * 8
+
+
+def test_rotation_matrices_match_reference_fixture_and_oracle():
+    gold = helpers.load_golden("reference_rotations.npz")
+    rots = cases.rotation_sweep(257)
+    assert np.array_equal(_prep.rotation_matrices_host(rots, False).numpy(), gold["z_up"])
+    assert np.array_equal(_prep.rotation_matrices_host(rots, True).numpy(), gold["z_down"])
+    more = cases.rotation_sweep(2000, seed=123)
+    for z in (False, True):
+        assert torch.equal(_prep.rotation_matrices_host(more, z), O.rotation_matrices(more, z))
+
+
+def test_matrix_prep_matches_oracle():
+    rots = cases.rotation_sweep(9)
+    a = _prep.mats_for("equi2pers", rots, False, CPU, (48, 64, 90.0, 0.0)).view(-1, 3, 3)
+    assert torch.equal(a, O.equi2pers_matrix(rots, False, 48, 64, 90.0, 0.0))
+    a = _prep.mats_for("pers2equi", rots, True, CPU, (48, 64, 70.0, 0.1)).view(-1, 3, 3)
+    assert torch.equal(a, O.pers2equi_matrix(rots, True, 48, 64, 70.0, 0.1))
+    a = _prep.mats_for("rot", rots, True, CPU).view(-1, 3, 3)
+    assert torch.equal(a, O.rotation_matrices(rots, True))
+
+
+def test_tables_match_oracle():
+    tx, ty = _prep.equirect_tables(48, 96, CPU)
+    cphi, sphi, cth, sth = O._equirect_ray_tables(48, 96)
+    assert torch.equal(tx, torch.cat([cth, sth]))
+    assert torch.equal(ty, torch.cat([cphi, sphi]))
+    tx, ty, itx = _prep.cube2equi_tables(64, 128, CPU)
+    t = O.cube2equi_tables(64, 128)
+    assert torch.equal(tx, torch.cat([t["tanx"], t["cosx"], t["sinth"], t["costh"]]))
+    assert torch.equal(ty, torch.cat([t["ntan"], t["cu"], t["cd"]]))
+    assert torch.equal(itx, torch.cat([t["face"], t["thr"]]).to(torch.int32))
+
+
+def test_caches_are_bounded_and_reused():
+    _prep.clear_caches()
+    a = _prep.equirect_tables(8, 16, CPU)
+    assert _prep.equirect_tables(8, 16, CPU) is a
+    for h in range(8, 8 + 2 * _prep.TABLE_CACHE_MAXSIZE, 1):
+        _prep.equirect_tables(h, 16, CPU)
+    assert len(_prep._tables) <= _prep.TABLE_CACHE_MAXSIZE
+    r1 = cases.rotation_sweep(4)
+    m = _prep.mats_for("rot", r1, False, CPU)
+    assert _prep.mats_for("rot", [dict(r) for r in r1], False, CPU) is m
+    assert _prep.mats_for("rot", r1, True, CPU) is not m
+
+
+ROT = {"roll": 0.0, "pitch": 0.0, "yaw": 0.0}
+
+
+def test_api_surface_matches_reference_names():
+    for n in ("Equi2Pers", "Equi2Equi", "Equi2Cube", "Cube2Equi", "Pers2Equi", "equi2pers",
+              "equi2equi", "equi2cube", "cube2equi", "pers2equi"):
+        assert hasattr(equilib_b200, n)
+    import inspect
+
+    sig = inspect.signature(equilib_b200.equi2pers)
+    assert list(sig.parameters)[:9] == ["equi", "rots", "height", "width", "fov_x", "skew",
+                                        "mode", "z_down", "clip_output"]
+    sig = inspect.signature(equilib_b200.equi2equi)
+    assert list(sig.parameters)[:7] == ["src", "rots", "clip_output", "mode", "z_down", "height",
+                                        "width"]
+    sig = inspect.signature(equilib_b200.equi2cube)
+    assert list(sig.parameters)[:7] == ["equi", "rots", "w_face", "cube_format", "z_down",
+                                        "clip_output", "mode"]
+    sig = inspect.signature(equilib_b200.cube2equi)
+    assert list(sig.parameters)[:6] == ["cubemap", "cube_format", "height", "width",
+                                        "clip_output", "mode"]
+    sig = inspect.signature(equilib_b200.pers2equi)
+    assert list(sig.parameters)[:9] == ["pers", "rots", "height", "width", "fov_x", "skew",
+                                        "mode", "z_down", "clip_output"]
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(3, 8, 16)
+    with pytest.raises(ValueError, match="no CPU path"):
+        equilib_b200.equi2equi(x, ROT)
+    with pytest.raises(ValueError, match="numpy"):
+        equilib_b200.equi2pers(np.zeros((3, 8, 16), np.float32), ROT, 4, 4, 90.0)
+    with pytest.raises(ValueError):
+        equilib_b200.equi2cube("nope", ROT, 4, "dice")
+    with pytest.raises(ValueError, match="no CPU path"):
+        equilib_b200.cube2equi({k: torch.zeros(3, 4, 4) for k in "FRBLUD"}, "dict", 8, 16)
+    with pytest.raises(AssertionError):
+        equilib_b200.cube2equi(torch.zeros(3, 4, 24), "horizon", 10, 16)  # not multiples of 8
+
+
+def test_product_never_imports_oracle_or_grid_sample():
+    pkg = os.path.join(ROOT, "equilib_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            code = re.sub(r'""".*?"""', "", src, flags=re.S)
+            code = re.sub(r"#.*", "", code)
+            assert "oracle" not in code, fn
+            assert "F.grid_sample" not in code and "functional" not in code, fn
