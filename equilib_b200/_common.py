@@ -104,7 +104,13 @@ def clip_tensor(src: torch.Tensor, mode: str, clip_output: bool, exact_clip: boo
 
 
 def flags_of(dtype: torch.dtype, saturate_uint8: bool) -> int:
-    return _lib.FLAG_SATURATE_U8 if (saturate_uint8 and dtype == torch.uint8) else 0
+    flags = _lib.FLAG_SATURATE_U8 if (saturate_uint8 and dtype == torch.uint8) else 0
+    # experiments only: EQUILIB_B200_WARP_SHAPE = 1 (32x1), 2 (16x2), 3 (8x4) forces the
+    # warp tile shape; unset/0 lets the library choose
+    ws = os.environ.get("EQUILIB_B200_WARP_SHAPE")
+    if ws:
+        flags |= (int(ws) & 3) << _lib.FLAG_WARP_SHAPE_SHIFT
+    return flags
 
 
 def mode_code(mode: str) -> int:

@@ -22,6 +22,8 @@ NEAREST, BILINEAR, BICUBIC = range(3)
 U8, F16, BF16, F32 = range(4)
 FLAG_SATURATE_U8 = 1
 FLAG_NORM_DIV = 2
+FLAG_LIBM = 4
+FLAG_WARP_SHAPE_SHIFT = 8
 
 MODES = {"nearest": NEAREST, "bilinear": BILINEAR, "bicubic": BICUBIC}
 

@@ -141,10 +141,10 @@ def minmax(img: Tensor, out2: Tensor) -> None:
 
 def coords(coords_out: Tensor, mats, tab_x, tab_y, itab_x, grid, transform: int, batch: int,
            src_h: int, src_w: int, dst_h: int, dst_w: int, grid_stride_b: int = 0, w_face: int = 0,
-           n_cells: int = 0) -> None:
+           n_cells: int = 0, flags: int = 0) -> None:
     """eqb_remap_coords: the transform's sampling grid (B, 2, dst_h, dst_w), for tests."""
     _require_cuda(coords_out, "coords_out")
-    d = _fill_desc(None, None, mats, tab_x, tab_y, itab_x, grid, None, transform, 0, 0, batch, 1,
+    d = _fill_desc(None, None, mats, tab_x, tab_y, itab_x, grid, None, transform, 0, flags, batch, 1,
                    src_h, src_w, dst_h, dst_w, (0, 0, 0), (0, 0, 0), grid_stride_b, w_face,
                    n_cells, [0] * 12, None)
     with torch.cuda.device(coords_out.device):

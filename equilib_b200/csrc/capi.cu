@@ -31,7 +31,10 @@ static size_t elt_size(int dtype) {
   return 0;
 }
 
-static int vec_px(int dtype, int mode) { return (dtype == EQB_U8 && mode != EQB_BICUBIC) ? 4 : 2; }
+static int vec_px(int dtype, int mode) {
+  if (mode == EQB_BICUBIC) return 1;
+  return dtype == EQB_U8 ? 4 : 2;
+}
 
 // Common validation + Params fill.  `need_images` is false for eqb_remap_coords.
 static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
@@ -43,7 +46,7 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
   if (d->dst_h <= 0 || d->dst_w <= 0 || d->src_h < 2 || d->src_w < 2)
     return fail(EQB_ERR_INVALID, "bad sizes: src %dx%d (each must be >= 2), dst %dx%d", d->src_h,
                 d->src_w, d->dst_h, d->dst_w);
-  if ((d->dst_h + kTileH - 1) / kTileH > 65535)
+  if (d->dst_h > 65535 * kWarps)
     return fail(EQB_ERR_INVALID, "dst_h %d too large", d->dst_h);
   std::memset(&p, 0, sizeof(p));
   p.B = d->batch;
@@ -61,6 +64,10 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
   p.clip = d->clip;
   p.inv_wm1 = 1.0f / (float)(d->src_w - 1);
   p.inv_hm1 = 1.0f / (float)(d->src_h - 1);
+  p.shf = (float)d->src_h;
+  p.swf = (float)d->src_w;
+  p.inv_wface = d->w_face > 0 ? 1.0f / (float)d->w_face : 0.0f;
+  p.iters = 1;
   p.w_face = d->w_face;
   p.n_cells = d->n_cells;
   p.flags = d->flags;
@@ -133,9 +140,17 @@ static int pick_px(const eqb_remap_desc* d) {
   return v;
 }
 
+// Warp tile shape: 0 = 32x1, 1 = 16x2, 2 = 8x4 lanes.  Forced through the flags for
+// experiments, otherwise picked per transform (DESIGN.md "warp tile").
+static int pick_ws(const eqb_remap_desc* d) {
+  const unsigned forced = (d->flags >> EQB_FLAG_WARP_SHAPE_SHIFT) & 3u;
+  if (forced) return (int)forced - 1;
+  return 1;
+}
+
 template <int XF> static cudaError_t go(const Params& p, const eqb_remap_desc* d, int px,
                                         cudaStream_t s) {
-  return launch_remap<XF>(p, d->mode, d->dtype, px, s);
+  return launch_remap<XF>(p, d->mode, d->dtype, px, pick_ws(d), s);
 }
 
 // ---------------------------------------------------------------------------
@@ -244,15 +259,16 @@ int32_t eqb_remap_coords(const eqb_remap_desc* d, float* coords_out, void* strea
   if (rc != EQB_OK) return rc;
   if (!coords_out) return fail(EQB_ERR_INVALID, "coords_out is null");
   p.coords_out = coords_out;
+  const bool libm = (d->flags & EQB_FLAG_LIBM) != 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
   switch (d->transform) {
-    case EQB_EQUI2EQUI: e = launch_coords<EQB_EQUI2EQUI>(p, s); break;
-    case EQB_EQUI2PERS: e = launch_coords<EQB_EQUI2PERS>(p, s); break;
-    case EQB_EQUI2CUBE: e = launch_coords<EQB_EQUI2CUBE>(p, s); break;
-    case EQB_CUBE2EQUI: e = launch_coords<EQB_CUBE2EQUI>(p, s); break;
-    case EQB_PERS2EQUI: e = launch_coords<EQB_PERS2EQUI>(p, s); break;
-    default: e = launch_coords<EQB_GRID>(p, s); break;
+    case EQB_EQUI2EQUI: e = launch_coords<EQB_EQUI2EQUI>(p, libm, s); break;
+    case EQB_EQUI2PERS: e = launch_coords<EQB_EQUI2PERS>(p, libm, s); break;
+    case EQB_EQUI2CUBE: e = launch_coords<EQB_EQUI2CUBE>(p, libm, s); break;
+    case EQB_CUBE2EQUI: e = launch_coords<EQB_CUBE2EQUI>(p, libm, s); break;
+    case EQB_PERS2EQUI: e = launch_coords<EQB_PERS2EQUI>(p, libm, s); break;
+    default: e = launch_coords<EQB_GRID>(p, libm, s); break;
   }
   if (e != cudaSuccess)
     return fail(EQB_ERR_CUDA, "coords launch failed: %s", cudaGetErrorString(e));

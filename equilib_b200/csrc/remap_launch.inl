@@ -1,57 +1,74 @@
 // Included by remap_xf<N>.cu with EQB_XF defined: instantiates the kernels of one
-// transform and its mode/dtype/PX dispatch (one translation unit per transform so
-// the six compile in parallel).
+// transform and its mode/dtype/PX/warp-shape dispatch (one translation unit per
+// transform so the six compile in parallel).
 #include "remap_kernels.cuh"
 
 namespace eqb {
 
 // Pixels per thread (= store width) instantiated per dtype and mode; must agree
-// with vec_px() in capi.cu.  uint8 bicubic stays at 2 (4 would need 250 registers).
+// with vec_px() in capi.cu.  Bicubic keeps one pixel per thread (16 taps of state).
 template <typename T, int MODE> struct VecPX { static constexpr int value = 2; };
 template <> struct VecPX<uint8_t, EQB_NEAREST> { static constexpr int value = 4; };
 template <> struct VecPX<uint8_t, EQB_BILINEAR> { static constexpr int value = 4; };
+template <typename T> struct VecPX<T, EQB_BICUBIC> { static constexpr int value = 1; };
 
-template <int XF, int MODE, typename T, int PX>
-static cudaError_t launch_one(const Params& p, cudaStream_t stream) {
-  const dim3 block(kTileW, kTileH);
-  const dim3 grid((p.dw + kTileW * PX - 1) / (kTileW * PX), (p.dh + kTileH - 1) / kTileH, p.B);
-  remap_kernel<XF, MODE, T, PX><<<grid, block, 0, stream>>>(p);
+template <int XF, int MODE, typename T, int PX, int WS>
+static cudaError_t launch_one(Params p, cudaStream_t stream) {
+  constexpr int LW = 32 >> WS, LH = 1 << WS;
+  const int tile_w = LW * PX, tile_h = LH * kWarps;
+  const long long tiles_x = (p.dw + tile_w - 1) / tile_w;
+  const long long ctas1 = tiles_x * ((p.dh + tile_h - 1) / tile_h) * p.B;
+  // walk several tiles per thread once the grid is large enough to fill the GPU
+  // many times over; small launches keep one tile per thread for parallelism
+  p.iters = ctas1 >= 148ll * 64 ? 4 : 1;
+  const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters),
+                  (unsigned)((p.dh + tile_h - 1) / tile_h), (unsigned)p.B);
+  remap_kernel<XF, MODE, T, PX, WS><<<grid, kWarps * 32, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
+template <int XF, int MODE, typename T, int PX>
+static cudaError_t launch_ws(const Params& p, int ws, cudaStream_t stream) {
+  switch (ws) {
+    case 0: return launch_one<XF, MODE, T, PX, 0>(p, stream);
+    case 1: return launch_one<XF, MODE, T, PX, 1>(p, stream);
+    default: return launch_one<XF, MODE, T, PX, 2>(p, stream);
+  }
+}
+
 template <int XF, int MODE, typename T>
-static cudaError_t launch_px(const Params& p, int px, cudaStream_t stream) {
-  if (px == 1) return launch_one<XF, MODE, T, 1>(p, stream);
-  return launch_one<XF, MODE, T, VecPX<T, MODE>::value>(p, stream);
+static cudaError_t launch_px(const Params& p, int px, int ws, cudaStream_t stream) {
+  if (px == 1) return launch_ws<XF, MODE, T, 1>(p, ws, stream);
+  return launch_ws<XF, MODE, T, VecPX<T, MODE>::value>(p, ws, stream);
 }
 
 template <int XF, int MODE>
-static cudaError_t launch_dtype(const Params& p, int dtype, int px, cudaStream_t stream) {
+static cudaError_t launch_dtype(const Params& p, int dtype, int px, int ws, cudaStream_t stream) {
   switch (dtype) {
-    case EQB_U8: return launch_px<XF, MODE, uint8_t>(p, px, stream);
-    case EQB_F16: return launch_px<XF, MODE, __half>(p, px, stream);
-    case EQB_BF16: return launch_px<XF, MODE, __nv_bfloat16>(p, px, stream);
-    case EQB_F32: return launch_px<XF, MODE, float>(p, px, stream);
+    case EQB_U8: return launch_px<XF, MODE, uint8_t>(p, px, ws, stream);
+    case EQB_F16: return launch_px<XF, MODE, __half>(p, px, ws, stream);
+    case EQB_BF16: return launch_px<XF, MODE, __nv_bfloat16>(p, px, ws, stream);
+    case EQB_F32: return launch_px<XF, MODE, float>(p, px, ws, stream);
   }
   return cudaErrorInvalidValue;
 }
 
 template <>
-cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px,
+cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px, int ws,
                                  cudaStream_t stream) {
   switch (mode) {
-    case EQB_NEAREST: return launch_dtype<EQB_XF, EQB_NEAREST>(p, dtype, px, stream);
-    case EQB_BILINEAR: return launch_dtype<EQB_XF, EQB_BILINEAR>(p, dtype, px, stream);
-    case EQB_BICUBIC: return launch_dtype<EQB_XF, EQB_BICUBIC>(p, dtype, px, stream);
+    case EQB_NEAREST: return launch_dtype<EQB_XF, EQB_NEAREST>(p, dtype, px, ws, stream);
+    case EQB_BILINEAR: return launch_dtype<EQB_XF, EQB_BILINEAR>(p, dtype, px, ws, stream);
+    case EQB_BICUBIC: return launch_dtype<EQB_XF, EQB_BICUBIC>(p, dtype, px, ws, stream);
   }
   return cudaErrorInvalidValue;
 }
 
 template <>
-cudaError_t launch_coords<EQB_XF>(const Params& p, cudaStream_t stream) {
-  const dim3 block(kTileW, kTileH);
-  const dim3 grid((p.dw + kTileW - 1) / kTileW, (p.dh + kTileH - 1) / kTileH, p.B);
-  coords_kernel<EQB_XF><<<grid, block, 0, stream>>>(p);
+cudaError_t launch_coords<EQB_XF>(const Params& p, bool libm, cudaStream_t stream) {
+  const dim3 grid((p.dw + 31) / 32, (p.dh + 7) / 8, p.B);
+  if (libm) coords_kernel<EQB_XF, true><<<grid, 256, 0, stream>>>(p);
+  else coords_kernel<EQB_XF, false><<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

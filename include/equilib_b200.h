@@ -63,6 +63,11 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 #define EQB_FLAG_SATURATE_U8 1u /* uint8 store saturates instead of wrapping mod 256 */
 #define EQB_FLAG_NORM_DIV 2u    /* normalise with a true division (reference CPU     \
                                    flavour) instead of a reciprocal multiply (CUDA)  */
+#define EQB_FLAG_LIBM 4u        /* eqb_remap_coords only: CUDA math-library sqrt /    \
+                                   div / atan2 instead of their inlined fast paths   */
+/* bits 8..9: force the warp tile shape (0 = auto, 1 = 32x1, 2 = 16x2, 3 = 8x4 lanes) */
+#define EQB_FLAG_WARP_SHAPE_SHIFT 8
+#define EQB_FLAG_WARP_SHAPE(n) ((uint32_t)(n) << EQB_FLAG_WARP_SHAPE_SHIFT)
 
 /*
  * One remap launch.  Images are planar NCHW views with unit inner stride;
