@@ -21,7 +21,6 @@ EQUI2EQUI, EQUI2PERS, EQUI2CUBE, CUBE2EQUI, PERS2EQUI, GRID = range(6)
 NEAREST, BILINEAR, BICUBIC = range(3)
 U8, F16, BF16, F32 = range(4)
 FLAG_SATURATE_U8 = 1
-FLAG_NORM_DIV = 2
 FLAG_LIBM = 4
 FLAG_WARP_SHAPE_SHIFT = 8
 

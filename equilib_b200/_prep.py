@@ -158,8 +158,8 @@ def mats_for(kind: str, rots: Sequence[Dict[str, float]], z_down: bool, device: 
 
 
 def equirect_tables(height: int, width: int, device: torch.device):
-    """(tab_x, tab_y) for an equirect *output*: [cos(theta)|sin(theta)] (2W) and
-    [cos(phi)|sin(phi)] (2H), theta = x*2*pi/W - pi, phi = y*pi/H - pi/2."""
+    """(tab_x, tab_y) for an equirect *output*: W interleaved (cos(theta), sin(theta))
+    pairs and [cos(phi)|sin(phi)] (2H), theta = x*2*pi/W - pi, phi = y*pi/H - pi/2."""
     key = ("equirect", height, width, device.type, device.index)
 
     def build():
@@ -167,7 +167,7 @@ def equirect_tables(height: int, width: int, device: torch.device):
         ys = torch.linspace(0, height - 1, height, dtype=F32)
         theta = xs * 2 * _PI / width - _PI
         phi = ys * _PI / height - _PI / 2
-        tx = torch.cat([torch.cos(theta), torch.sin(theta)])
+        tx = torch.stack([torch.cos(theta), torch.sin(theta)], dim=1).reshape(-1).contiguous()
         ty = torch.cat([1 * torch.cos(phi), 1 * torch.sin(phi)])
         return tx.to(device), ty.to(device)
 

@@ -66,6 +66,8 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
   p.inv_hm1 = 1.0f / (float)(d->src_h - 1);
   p.shf = (float)d->src_h;
   p.swf = (float)d->src_w;
+  p.shm1f = (float)(d->src_h - 1);
+  p.swm1f = (float)(d->src_w - 1);
   p.inv_wface = d->w_face > 0 ? 1.0f / (float)d->w_face : 0.0f;
   p.iters = 1;
   p.w_face = d->w_face;

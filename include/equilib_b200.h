@@ -61,8 +61,6 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 
 /* flags */
 #define EQB_FLAG_SATURATE_U8 1u /* uint8 store saturates instead of wrapping mod 256 */
-#define EQB_FLAG_NORM_DIV 2u    /* normalise with a true division (reference CPU     \
-                                   flavour) instead of a reciprocal multiply (CUDA)  */
 #define EQB_FLAG_LIBM 4u        /* eqb_remap_coords only: CUDA math-library sqrt /    \
                                    div / atan2 instead of their inlined fast paths   */
 /* bits 8..9: force the warp tile shape (0 = auto, 1 = 32x1, 2 = 16x2, 3 = 8x4 lanes) */
@@ -76,8 +74,8 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
  *
  * Per transform:
  *   EQUI2EQUI  src = equirect (src_h x src_w), dst = equirect (dst_h x dst_w).
- *              mats = B x 9 (R).  tab_x = [cos(theta) | sin(theta)] (2*dst_w),
- *              tab_y = [cos(phi) | sin(phi)] (2*dst_h).
+ *              mats = B x 9 (R).  tab_x = dst_w interleaved (cos(theta), sin(theta))
+ *              pairs (8-byte aligned), tab_y = [cos(phi) | sin(phi)] (2*dst_h).
  *   EQUI2PERS  src = equirect, dst = perspective.  mats = B x 9 (R @ G).
  *   EQUI2CUBE  src = equirect, dst = cube canvas.  mats = B x 9 (R).
  *              tab_x = rng (w_face).  dst_h = w_face, dst_w = n_cells * w_face:
