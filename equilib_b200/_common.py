@@ -30,14 +30,34 @@ def check_backend(kwargs: dict) -> None:
         )
 
 
-def pop_options(kwargs: dict) -> Tuple[bool, bool]:
-    """Extensions over the reference API (both default to reference behaviour /
-    the documented policy): ``exact_clip`` and ``saturate_uint8``."""
-    exact_clip = bool(kwargs.pop("exact_clip", os.environ.get("EQUILIB_B200_EXACT_CLIP") == "1"))
-    saturate = bool(kwargs.pop("saturate_uint8", False))
+class Options:
+    """Extensions over the reference API; all default to the reference's behaviour /
+    the documented policy.
+
+    exact_clip      run the global min/max pass also where it is a <= 2 ulp no-op
+    saturate_uint8  saturate the uint8 store instead of wrapping like the reference
+    clip_group      torch.distributed group over which the clip range is all-reduced
+                    (sharded batches, equilib_b200/sharded.py)
+    """
+
+    __slots__ = ("exact_clip", "saturate_uint8", "clip_group")
+
+    def __init__(self, exact_clip=False, saturate_uint8=False, clip_group=None):
+        self.exact_clip = exact_clip
+        self.saturate_uint8 = saturate_uint8
+        self.clip_group = clip_group
+
+
+def pop_options(kwargs: dict) -> Options:
+    opt = Options(
+        exact_clip=bool(kwargs.pop("exact_clip",
+                                   os.environ.get("EQUILIB_B200_EXACT_CLIP") == "1")),
+        saturate_uint8=bool(kwargs.pop("saturate_uint8", False)),
+        clip_group=kwargs.pop("clip_group", None),
+    )
     if kwargs:
         raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
-    return exact_clip, saturate
+    return opt
 
 
 def require_cuda_tensor(x, name: str) -> None:
@@ -84,7 +104,7 @@ def normalise_single(img: torch.Tensor, rots: Rot):
 
 
 def clip_tensor(src: torch.Tensor, mode: str, clip_output: bool, exact_clip: bool,
-                always: bool = False) -> Optional[torch.Tensor]:
+                always: bool = False, group=None) -> Optional[torch.Tensor]:
     """Device tensor {lo, hi} for ``torch.clip(out, torch.min(src), torch.max(src))``
     (e.g. equilib/equi2equi/torch.py:195-198), or None when no clamp is launched.
 
@@ -100,7 +120,16 @@ def clip_tensor(src: torch.Tensor, mode: str, clip_output: bool, exact_clip: boo
         return None
     out2 = torch.empty(2, dtype=torch.float32, device=src.device)
     _ops.minmax(src, out2)
-    return out2
+    return reduce_clip(out2, group)
+
+
+def reduce_clip(out2: torch.Tensor, group) -> torch.Tensor:
+    """All-reduce a (min, max) pair over ``group`` (no-op without one)."""
+    if group is None:
+        return out2
+    from .sharded import allreduce_minmax
+
+    return allreduce_minmax(out2, None if group is True else group)
 
 
 def flags_of(dtype: torch.dtype, saturate_uint8: bool) -> int:

@@ -101,9 +101,9 @@ def cube2equi(
     )
     K.require_cuda_tensor(leaf, "cubemap")
     K.check_backend(kwargs)
-    exact_clip, saturate = K.pop_options(kwargs)
+    opt = K.pop_options(kwargs)
     out = run(cubemap, cube_format, height=height, width=width, mode=mode,
-              clip_output=clip_output, exact_clip=exact_clip, saturate_uint8=saturate)
+              clip_output=clip_output, opt=opt)
     if out.shape[0] == 1:
         out = out.squeeze(0)
     return out
@@ -121,9 +121,11 @@ def _minmax_views(views, device) -> torch.Tensor:
     return torch.stack([st[:, 0].min(), st[:, 1].max()])
 
 
-def run(cubemap, cube_format, height, width, mode, clip_output=True, exact_clip=False,
-        saturate_uint8=False) -> torch.Tensor:
+def run(cubemap, cube_format, height, width, mode, clip_output=True,
+        opt: K.Options = None) -> torch.Tensor:
     """Replaces convert2horizon + equilib/cube2equi/torch.py:248-357."""
+    opt = opt or K.Options()
+    exact_clip = opt.exact_clip
     K.mode_code(mode)
     face_ptrs = None
     if cube_format in ("horizon", "dice"):
@@ -185,11 +187,11 @@ def run(cubemap, cube_format, height, width, mode, clip_output=True, exact_clip=
     tab_x, tab_y, itab_x = _prep.cube2equi_tables(height, width, dev)
     clip = None
     if src.dtype != torch.uint8 and clip_output and (exact_clip or mode == "bicubic"):
-        clip = _minmax_views(clip_views, dev)
+        clip = K.reduce_clip(_minmax_views(clip_views, dev), opt.clip_group)
     out = torch.empty((bs, c, height, width), dtype=src.dtype, device=dev)
     K.launch(
         src, out, transform=_lib.CUBE2EQUI, mode=mode,
-        flags=K.flags_of(src.dtype, saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(src.dtype, opt.saturate_uint8), batch=bs, channels=c,
         src_hw=(w, 6 * w), dst_hw=(height, width),
         src_strides=src_strides, dst_strides=out.stride()[:3],
         tab_x=tab_x, tab_y=tab_y, itab_x=itab_x, clip=clip,

@@ -74,18 +74,18 @@ def equi2cube(
 ):
     K.require_cuda_tensor(equi, "equi")
     K.check_backend(kwargs)
-    exact_clip, saturate = K.pop_options(kwargs)
+    opt = K.pop_options(kwargs)
     equi, rots, is_single = K.normalise_single(equi, rots)
     out = run(equi, rots, w_face=w_face, cube_format=cube_format, z_down=z_down, mode=mode,
-              clip_output=clip_output, exact_clip=exact_clip, saturate_uint8=saturate)
+              clip_output=clip_output, opt=opt)
     if is_single:
         out = out[0]
     return out
 
 
-def run(equi, rots, w_face, cube_format, z_down, mode, clip_output=True, exact_clip=False,
-        saturate_uint8=False):
+def run(equi, rots, w_face, cube_format, z_down, mode, clip_output=True, opt: K.Options = None):
     """Replaces equilib/equi2cube/torch.py:103-253 with one fused launch."""
+    opt = opt or K.Options()
     equi = K.check_image(equi, "equi")
     assert len(equi) == len(rots), (
         f"ERR: length of equi and rot differs: {len(equi)} vs {len(rots)}"
@@ -100,7 +100,7 @@ def run(equi, rots, w_face, cube_format, z_down, mode, clip_output=True, exact_c
     # the reference flips z_down for this transform (equi2cube/torch.py:206-209)
     mats = _prep.mats_for("rot", rots, not z_down, dev)
     rng = _prep.cube_rng_table(w, dev)
-    clip = K.clip_tensor(equi, mode, clip_output, exact_clip)
+    clip = K.clip_tensor(equi, mode, clip_output, opt.exact_clip, group=opt.clip_group)
 
     if cube_format == "horizon":
         out = torch.empty((bs, c, w, 6 * w), dtype=equi.dtype, device=dev)
@@ -117,7 +117,7 @@ def run(equi, rots, w_face, cube_format, z_down, mode, clip_output=True, exact_c
 
     K.launch(
         equi, out, transform=_lib.EQUI2CUBE, mode=mode,
-        flags=K.flags_of(equi.dtype, saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(equi.dtype, opt.saturate_uint8), batch=bs, channels=c,
         src_hw=(h_equi, w_equi), dst_hw=(w, len(cells) * w),
         src_strides=equi.stride()[:3], dst_strides=strides,
         mats=mats, tab_x=rng, clip=clip, w_face=w, n_cells=len(cells), cell_offset=cells,

@@ -60,18 +60,19 @@ def equi2equi(
 ) -> torch.Tensor:
     K.require_cuda_tensor(src, "src")
     K.check_backend(kwargs)
-    exact_clip, saturate = K.pop_options(kwargs)
+    opt = K.pop_options(kwargs)
     src, rots, is_single = K.normalise_single(src, rots)
     out = run(src, rots, z_down=z_down, mode=mode, height=height, width=width,
-              clip_output=clip_output, exact_clip=exact_clip, saturate_uint8=saturate)
+              clip_output=clip_output, opt=opt)
     if is_single:
         out = out.squeeze(0)
     return out
 
 
-def run(src, rots, z_down, mode, height=None, width=None, clip_output=True, exact_clip=False,
-        saturate_uint8=False) -> torch.Tensor:
+def run(src, rots, z_down, mode, height=None, width=None, clip_output=True,
+        opt: K.Options = None) -> torch.Tensor:
     """Replaces equilib/equi2equi/torch.py:45-200 with one fused launch."""
+    opt = opt or K.Options()
     src = K.check_image(src, "src")
     assert len(src) == len(rots), (
         f"ERR: length of `src` and `rot` differs: {len(src)} vs {len(rots)}"
@@ -89,10 +90,10 @@ def run(src, rots, z_down, mode, height=None, width=None, clip_output=True, exac
     dev = src.device
     mats = _prep.mats_for("rot", rots, z_down, dev)
     tab_x, tab_y = _prep.equirect_tables(height, width, dev)
-    clip = K.clip_tensor(src, mode, clip_output, exact_clip)
+    clip = K.clip_tensor(src, mode, clip_output, opt.exact_clip, group=opt.clip_group)
     out = torch.empty((bs, c, height, width), dtype=src.dtype, device=dev)
     K.launch(
-        src, out, transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, saturate_uint8),
+        src, out, transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, opt.saturate_uint8),
         batch=bs, channels=c, src_hw=(h_equi, w_equi), dst_hw=(height, width),
         src_strides=src.stride()[:3], dst_strides=out.stride()[:3],
         mats=mats, tab_x=tab_x, tab_y=tab_y, clip=clip,

@@ -69,18 +69,19 @@ def equi2pers(
 ) -> torch.Tensor:
     K.require_cuda_tensor(equi, "equi")
     K.check_backend(kwargs)
-    exact_clip, saturate = K.pop_options(kwargs)
+    opt = K.pop_options(kwargs)
     equi, rots, is_single = K.normalise_single(equi, rots)
     out = run(equi, rots, height=height, width=width, fov_x=fov_x, skew=skew, z_down=z_down,
-              mode=mode, clip_output=clip_output, exact_clip=exact_clip, saturate_uint8=saturate)
+              mode=mode, clip_output=clip_output, opt=opt)
     if is_single:
         out = out.squeeze(0)
     return out
 
 
 def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
-        exact_clip=False, saturate_uint8=False) -> torch.Tensor:
+        opt: K.Options = None) -> torch.Tensor:
     """Replaces equilib/equi2pers/torch.py:96-244 with one fused launch."""
+    opt = opt or K.Options()
     equi = K.check_image(equi, "equi")
     assert len(equi) == len(rots), (
         f"ERR: length of equi and rot differs: {len(equi)} vs {len(rots)}"
@@ -90,11 +91,11 @@ def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
     dev = equi.device
     mats = _prep.mats_for("equi2pers", rots, z_down, dev,
                           (int(height), int(width), float(fov_x), float(skew)))
-    clip = K.clip_tensor(equi, mode, clip_output, exact_clip)
+    clip = K.clip_tensor(equi, mode, clip_output, opt.exact_clip, group=opt.clip_group)
     out = torch.empty((bs, c, height, width), dtype=equi.dtype, device=dev)
     K.launch(
         equi, out, transform=_lib.EQUI2PERS, mode=mode,
-        flags=K.flags_of(equi.dtype, saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(equi.dtype, opt.saturate_uint8), batch=bs, channels=c,
         src_hw=(h_equi, w_equi), dst_hw=(height, width),
         src_strides=equi.stride()[:3], dst_strides=out.stride()[:3], mats=mats, clip=clip,
     )

@@ -63,20 +63,21 @@ def pers2equi(
 ) -> torch.Tensor:
     K.require_cuda_tensor(pers, "pers")
     K.check_backend(kwargs)
-    exact_clip, saturate = K.pop_options(kwargs)
+    opt = K.pop_options(kwargs)
     pers, rots, is_single = K.normalise_single(pers, rots)
     out = run(pers, rots, height=height, width=width, fov_x=fov_x, skew=skew, z_down=z_down,
-              mode=mode, clip_output=clip_output, saturate_uint8=saturate)
+              mode=mode, clip_output=clip_output, opt=opt)
     if is_single:
         out = out.squeeze(0)
     return out
 
 
 def run(pers, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
-        saturate_uint8=False) -> torch.Tensor:
+        opt: K.Options = None) -> torch.Tensor:
     """Replaces equilib/pers2equi/torch.py:97-253.  Pixels outside the field of view
     are zeroed and *then* clipped (lines 246-251), so with clip_output they end up at
     clamp(0, min(pers), max(pers)); hence the min/max pass always runs for floats."""
+    opt = opt or K.Options()
     pers = K.check_image(pers, "pers")
     assert len(pers) == len(rots), (
         f"ERR: length of pers and rot differs: {len(pers)} vs {len(rots)}"
@@ -87,11 +88,12 @@ def run(pers, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
     mats = _prep.mats_for("pers2equi", rots, z_down, dev,
                           (int(h_pers), int(w_pers), float(fov_x), float(skew)))
     tab_x, tab_y = _prep.equirect_tables(height, width, dev)
-    clip = K.clip_tensor(pers, mode, clip_output, exact_clip=True, always=True)
+    clip = K.clip_tensor(pers, mode, clip_output, exact_clip=True, always=True,
+                         group=opt.clip_group)
     out = torch.empty((bs, c, height, width), dtype=pers.dtype, device=dev)
     K.launch(
         pers, out, transform=_lib.PERS2EQUI, mode=mode,
-        flags=K.flags_of(pers.dtype, saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(pers.dtype, opt.saturate_uint8), batch=bs, channels=c,
         src_hw=(h_pers, w_pers), dst_hw=(height, width),
         src_strides=pers.stride()[:3], dst_strides=out.stride()[:3],
         mats=mats, tab_x=tab_x, tab_y=tab_y, clip=clip,
