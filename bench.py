@@ -203,12 +203,20 @@ def main():
     ap.add_argument("--workload", default="e2e_4k_bf16_b32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stage", action="store_true",
+                    help="experiments: force the direct-gather kernel")
+    ap.add_argument("--exact-coords", action="store_true",
+                    help="experiments: exact coordinate chain on every pixel")
     ap.add_argument("--warp-shape", type=int, default=0,
                     help="experiments: force the warp tile (1=32x1, 2=16x2, 3=8x4 lanes)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.warp_shape:
         os.environ["EQUILIB_B200_WARP_SHAPE"] = str(args.warp_shape)
+    if args.no_stage:
+        os.environ["EQUILIB_B200_NO_STAGE"] = "1"
+    if args.exact_coords:
+        os.environ["EQUILIB_B200_FAST_COORDS"] = "0"
     if args.impl == "reference":
         return run_reference(args, wl)
 

@@ -38,14 +38,17 @@ class Options:
     saturate_uint8  saturate the uint8 store instead of wrapping like the reference
     clip_group      torch.distributed group over which the clip range is all-reduced
                     (sharded batches, equilib_b200/sharded.py)
+    fast_coords     None = library default (on for uint8 / fp16 / bf16 bilinear, off for
+                    fp32); True / False force the interpolated / exact coordinate chain
     """
 
-    __slots__ = ("exact_clip", "saturate_uint8", "clip_group")
+    __slots__ = ("exact_clip", "saturate_uint8", "clip_group", "fast_coords")
 
-    def __init__(self, exact_clip=False, saturate_uint8=False, clip_group=None):
+    def __init__(self, exact_clip=False, saturate_uint8=False, clip_group=None, fast_coords=None):
         self.exact_clip = exact_clip
         self.saturate_uint8 = saturate_uint8
         self.clip_group = clip_group
+        self.fast_coords = fast_coords
 
 
 def pop_options(kwargs: dict) -> Options:
@@ -54,6 +57,7 @@ def pop_options(kwargs: dict) -> Options:
                                    os.environ.get("EQUILIB_B200_EXACT_CLIP") == "1")),
         saturate_uint8=bool(kwargs.pop("saturate_uint8", False)),
         clip_group=kwargs.pop("clip_group", None),
+        fast_coords=kwargs.pop("fast_coords", None),
     )
     if kwargs:
         raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
@@ -132,13 +136,22 @@ def reduce_clip(out2: torch.Tensor, group) -> torch.Tensor:
     return allreduce_minmax(out2, None if group is True else group)
 
 
-def flags_of(dtype: torch.dtype, saturate_uint8: bool) -> int:
-    flags = _lib.FLAG_SATURATE_U8 if (saturate_uint8 and dtype == torch.uint8) else 0
+def flags_of(dtype: torch.dtype, opt: "Options") -> int:
+    flags = _lib.FLAG_SATURATE_U8 if (opt.saturate_uint8 and dtype == torch.uint8) else 0
+    fast = opt.fast_coords
+    if fast is None and os.environ.get("EQUILIB_B200_FAST_COORDS") in ("0", "1"):
+        fast = os.environ["EQUILIB_B200_FAST_COORDS"] == "1"
+    if fast is True:
+        flags |= _lib.FLAG_FAST_COORDS
+    elif fast is False:
+        flags |= _lib.FLAG_EXACT_COORDS
     # experiments only: EQUILIB_B200_WARP_SHAPE = 1 (32x1), 2 (16x2), 3 (8x4) forces the
     # warp tile shape; unset/0 lets the library choose
     ws = os.environ.get("EQUILIB_B200_WARP_SHAPE")
     if ws:
         flags |= (int(ws) & 3) << _lib.FLAG_WARP_SHAPE_SHIFT
+    if os.environ.get("EQUILIB_B200_NO_STAGE") == "1":
+        flags |= _lib.FLAG_NO_STAGE
     return flags
 
 

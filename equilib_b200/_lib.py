@@ -22,6 +22,9 @@ NEAREST, BILINEAR, BICUBIC = range(3)
 U8, F16, BF16, F32 = range(4)
 FLAG_SATURATE_U8 = 1
 FLAG_LIBM = 4
+FLAG_NO_STAGE = 8
+FLAG_EXACT_COORDS = 16
+FLAG_FAST_COORDS = 32
 FLAG_WARP_SHAPE_SHIFT = 8
 
 MODES = {"nearest": NEAREST, "bilinear": BILINEAR, "bicubic": BICUBIC}

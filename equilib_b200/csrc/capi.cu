@@ -150,8 +150,45 @@ static int pick_ws(const eqb_remap_desc* d) {
   return 1;
 }
 
+// The staged (shared-memory) kernel serves bilinear sampling from a plain image when
+// its 16-byte cp.async row chunks are aligned and the launch is large enough to pay
+// for the CTA-wide synchronisation; everything else takes the direct-gather kernel.
+static bool can_stage(const eqb_remap_desc* d, int px) {
+  if (d->flags & EQB_FLAG_NO_STAGE) return false;
+  if (d->mode != EQB_BILINEAR || d->transform == EQB_CUBE2EQUI) return false;
+  // fp32 with the exact coordinate chain is faster on the direct-gather kernel (4-byte
+  // gathers touch the same number of lines, and 80 registers leave 3 CTAs per SM)
+  if (d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS)) return false;
+  if (px != vec_px(d->dtype, d->mode)) return false;
+  const long long per16 = 16 / (long long)elt_size(d->dtype);
+  if (reinterpret_cast<uintptr_t>(d->src) % 16) return false;
+  if (d->src_stride_b % per16 || d->src_stride_c % per16 || d->src_stride_h % per16) return false;
+  if (d->src_w > 65536 || d->src_h > 65536) return false;
+  if (d->channels > 4) return false;
+  return (long long)d->batch * d->dst_h * d->dst_w >= (1ll << 18);
+}
+
+// Fast coordinates (exact chain on every 4th pixel + cubic interpolation) are the
+// default for 16- and 8-bit images, opt-in for fp32, and need 4-pixel vector stores.
+static bool can_fast(const eqb_remap_desc* d) {
+  if (d->transform > EQB_EQUI2CUBE) return false;
+  if (d->flags & EQB_FLAG_EXACT_COORDS) return false;
+  if (d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS)) return false;
+  const size_t bytes = 4 * elt_size(d->dtype);
+  if (reinterpret_cast<uintptr_t>(d->dst) % bytes) return false;
+  if (d->dst_stride_b % 4 || d->dst_stride_c % 4 || d->dst_stride_h % 4) return false;
+  if (d->transform == EQB_EQUI2CUBE) {
+    // a 16-lane row segment (64 pixels) must not straddle two faces
+    if (d->w_face % 64) return false;
+    for (int i = 0; i < d->n_cells; ++i)
+      if (d->cell_offset[i] % 4) return false;
+  }
+  return true;
+}
+
 template <int XF> static cudaError_t go(const Params& p, const eqb_remap_desc* d, int px,
                                         cudaStream_t s) {
+  if (can_stage(d, px)) return launch_staged<XF>(p, d->dtype, can_fast(d), s);
   return launch_remap<XF>(p, d->mode, d->dtype, px, pick_ws(d), s);
 }
 

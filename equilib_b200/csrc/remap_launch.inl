@@ -64,6 +64,56 @@ cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px, i
   return cudaErrorInvalidValue;
 }
 
+#if EQB_XF != 3  // not EQB_CUBE2EQUI (enum values are invisible to the preprocessor)
+template <int XF, typename T, int PX, bool FAST, bool CLIP>
+static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
+  using G = StagedGeom<PX>;
+  // 32 KB of tile per CTA (56 KB for 4-byte pixels): an output tile rotated by any
+  // angle away from the poles fits for C <= 3
+  const int smem = sizeof(T) == 4 ? 56 * 1024 : 32 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(remap_staged_kernel<XF, T, PX, FAST, CLIP>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  p.smem_elems = smem / (int)sizeof(T);
+  const long long tiles_x = (p.dw + G::tile_w - 1) / G::tile_w;
+  const long long tiles_y = (p.dh + G::tile_h - 1) / G::tile_h;
+  p.iters = tiles_x * tiles_y * p.B >= 148ll * 64 ? 4 : 1;
+  const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
+  remap_staged_kernel<XF, T, PX, FAST, CLIP><<<grid, kWarps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int XF, typename T, int PX, bool FAST>
+static cudaError_t launch_staged_one(const Params& p, cudaStream_t stream) {
+  if (p.clip) return launch_staged_clip<XF, T, PX, FAST, true>(p, stream);
+  return launch_staged_clip<XF, T, PX, FAST, false>(p, stream);
+}
+
+template <int XF, typename T, int PX>
+static cudaError_t launch_staged_t(const Params& p, bool fast, cudaStream_t stream) {
+#if EQB_XF <= 2  // transforms with a transcendental chain have a fast-coordinate variant
+  if (fast) return launch_staged_one<XF, T, 4, true>(p, stream);
+#endif
+  return launch_staged_one<XF, T, PX, false>(p, stream);
+}
+#endif
+
+template <>
+cudaError_t launch_staged<EQB_XF>(const Params& p, int dtype, bool fast, cudaStream_t stream) {
+#if EQB_XF != 3
+  switch (dtype) {
+    case EQB_U8: return launch_staged_t<EQB_XF, uint8_t, 4>(p, fast, stream);
+    case EQB_F16: return launch_staged_t<EQB_XF, __half, 2>(p, fast, stream);
+    case EQB_BF16: return launch_staged_t<EQB_XF, __nv_bfloat16, 2>(p, fast, stream);
+    case EQB_F32: return launch_staged_t<EQB_XF, float, 2>(p, fast, stream);
+  }
+#endif
+  return cudaErrorInvalidValue;
+}
+
 template <>
 cudaError_t launch_coords<EQB_XF>(const Params& p, bool libm, cudaStream_t stream) {
   const dim3 grid((p.dw + 31) / 32, (p.dh + 7) / 8, p.B);

@@ -191,7 +191,7 @@ def run(cubemap, cube_format, height, width, mode, clip_output=True,
     out = torch.empty((bs, c, height, width), dtype=src.dtype, device=dev)
     K.launch(
         src, out, transform=_lib.CUBE2EQUI, mode=mode,
-        flags=K.flags_of(src.dtype, opt.saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(src.dtype, opt), batch=bs, channels=c,
         src_hw=(w, 6 * w), dst_hw=(height, width),
         src_strides=src_strides, dst_strides=out.stride()[:3],
         tab_x=tab_x, tab_y=tab_y, itab_x=itab_x, clip=clip,

@@ -117,7 +117,7 @@ def run(equi, rots, w_face, cube_format, z_down, mode, clip_output=True, opt: K.
 
     K.launch(
         equi, out, transform=_lib.EQUI2CUBE, mode=mode,
-        flags=K.flags_of(equi.dtype, opt.saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(equi.dtype, opt), batch=bs, channels=c,
         src_hw=(h_equi, w_equi), dst_hw=(w, len(cells) * w),
         src_strides=equi.stride()[:3], dst_strides=strides,
         mats=mats, tab_x=rng, clip=clip, w_face=w, n_cells=len(cells), cell_offset=cells,

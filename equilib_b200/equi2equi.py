@@ -93,7 +93,7 @@ def run(src, rots, z_down, mode, height=None, width=None, clip_output=True,
     clip = K.clip_tensor(src, mode, clip_output, opt.exact_clip, group=opt.clip_group)
     out = torch.empty((bs, c, height, width), dtype=src.dtype, device=dev)
     K.launch(
-        src, out, transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, opt.saturate_uint8),
+        src, out, transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, opt),
         batch=bs, channels=c, src_hw=(h_equi, w_equi), dst_hw=(height, width),
         src_strides=src.stride()[:3], dst_strides=out.stride()[:3],
         mats=mats, tab_x=tab_x, tab_y=tab_y, clip=clip,

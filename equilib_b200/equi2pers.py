@@ -95,7 +95,7 @@ def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
     out = torch.empty((bs, c, height, width), dtype=equi.dtype, device=dev)
     K.launch(
         equi, out, transform=_lib.EQUI2PERS, mode=mode,
-        flags=K.flags_of(equi.dtype, opt.saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(equi.dtype, opt), batch=bs, channels=c,
         src_hw=(h_equi, w_equi), dst_hw=(height, width),
         src_strides=equi.stride()[:3], dst_strides=out.stride()[:3], mats=mats, clip=clip,
     )

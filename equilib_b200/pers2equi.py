@@ -93,7 +93,7 @@ def run(pers, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
     out = torch.empty((bs, c, height, width), dtype=pers.dtype, device=dev)
     K.launch(
         pers, out, transform=_lib.PERS2EQUI, mode=mode,
-        flags=K.flags_of(pers.dtype, opt.saturate_uint8), batch=bs, channels=c,
+        flags=K.flags_of(pers.dtype, opt), batch=bs, channels=c,
         src_hw=(h_pers, w_pers), dst_hw=(height, width),
         src_strides=pers.stride()[:3], dst_strides=out.stride()[:3],
         mats=mats, tab_x=tab_x, tab_y=tab_y, clip=clip,

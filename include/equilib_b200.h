@@ -63,6 +63,11 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 #define EQB_FLAG_SATURATE_U8 1u /* uint8 store saturates instead of wrapping mod 256 */
 #define EQB_FLAG_LIBM 4u        /* eqb_remap_coords only: CUDA math-library sqrt /    \
                                    div / atan2 instead of their inlined fast paths   */
+#define EQB_FLAG_NO_STAGE 8u    /* never use the shared-memory staged kernel           */
+#define EQB_FLAG_EXACT_COORDS 16u /* 16/8-bit images: exact coordinate chain on every     \
+                                    pixel (default: every 4th pixel + cubic interpolation \
+                                    along x, error ~1e-6 px)                   */
+#define EQB_FLAG_FAST_COORDS 32u  /* fp32 images: opt in to the interpolated coordinates  */
 /* bits 8..9: force the warp tile shape (0 = auto, 1 = 32x1, 2 = 16x2, 3 = 8x4 lanes) */
 #define EQB_FLAG_WARP_SHAPE_SHIFT 8
 #define EQB_FLAG_WARP_SHAPE(n) ((uint32_t)(n) << EQB_FLAG_WARP_SHAPE_SHIFT)

@@ -205,6 +205,93 @@ def test_warp_tile_shapes_are_equivalent(shape, monkeypatch):
     assert torch.equal(equilib_b200.equi2cube(u8, rots, 24, "dice"), ref)
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "uint8"])
+def test_staged_and_direct_kernels_agree(dtype, monkeypatch):
+    """Large bilinear launches take the shared-memory staged kernel (tiles whose source
+    box does not fit fall back to direct gathers inside it); EQUILIB_B200_NO_STAGE=1
+    forces the direct-gather kernel.  Same bits either way, poles and seam included."""
+    img = torch.from_numpy(cases.noise_image((3, 3, 512, 1024), "uint8" if dtype == "uint8"
+                                             else "float32", 5)).to(DEV)
+    if dtype == "bfloat16":
+        img = img.to(torch.bfloat16)
+    rots = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}, {"roll": 0.3, "pitch": -0.4, "yaw": 1.1},
+            {"roll": 1.5, "pitch": 1.2, "yaw": -2.9}]
+    def run_all():
+        kw = dict(fast_coords=False)  # same (exact) coordinate chain on both paths
+        return [
+            equilib_b200.equi2equi(img, rots, **kw),
+            equilib_b200.equi2pers(img, rots, 480, 640, 100.0, **kw),
+            equilib_b200.equi2cube(img, rots, 256, "dice", **kw),
+            equilib_b200.equi2cube(img, rots, 256, "horizon", **kw),
+            equilib_b200.pers2equi(img, rots, 512, 1024, 90.0, **kw),
+            equilib_b200.equi2equi(img[:, :, :, :1000], rots, height=500, width=1002, **kw),
+        ]
+    staged = run_all()
+    monkeypatch.setenv("EQUILIB_B200_NO_STAGE", "1")
+    direct = run_all()
+    for a, b in zip(staged, direct):
+        assert torch.equal(a, b)
+
+
+HARD_ROTS = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}, {"roll": 0.3, "pitch": -0.4, "yaw": 1.1},
+             {"roll": 1.5, "pitch": 1.2, "yaw": -2.9}, {"roll": -0.7, "pitch": 1.5707, "yaw": 3.1}]
+
+
+def test_fast_coordinates_error_in_pixels():
+    """Fast coordinates = exact chain on every 4th pixel + cubic interpolation along x.
+    Sampling a ramp image (pixel value == its own x or y) bilinearly returns the
+    sampling coordinate itself, so fast-vs-exact output differences ARE the coordinate
+    error in pixels.  Bound: 2e-3 px max, 2e-4 px mean at 2K x 4K (an fp32 coordinate
+    there resolves 2.4e-4 px; the reference's own fp32 chain is off by up to 0.23 px at
+    the poles vs float64, SURVEY probe B3).  The error is dominated by the skipped
+    normalise / un-normalise round trip (its own rounding noise), not the cubic."""
+    h, w = 2048, 4096
+    ys = torch.arange(h, dtype=torch.float32, device=DEV)[:, None].expand(h, w)
+    xs = torch.arange(w, dtype=torch.float32, device=DEV)[None, :].expand(h, w)
+    img = torch.stack([ys, xs])[None].expand(len(HARD_ROTS), -1, -1, -1).contiguous()
+    for fn, args in ((equilib_b200.equi2equi, ()), (equilib_b200.equi2pers, (1024, 1024, 90.0)),
+                     (equilib_b200.equi2cube, (512, "horizon"))):
+        exact = fn(img, HARD_ROTS, *args, clip_output=False, fast_coords=False)
+        fast = fn(img, HARD_ROTS, *args, clip_output=False, fast_coords=True)
+        dy = (fast[:, 0] - exact[:, 0]).abs()
+        dx = (fast[:, 1] - exact[:, 1]).abs()
+        # at the seam the exact path blends columns W-1 and 0 of the ramp: skip it
+        seam = (exact[:, 1] > w - 1.5) | (exact[:, 1] < 0.5) | (fast[:, 1] > w - 1.5)
+        dx = torch.where(seam, torch.zeros_like(dx), dx)
+        print(f"{fn.__name__}: coordinate error max dy {float(dy.max()):.2e} dx {float(dx.max()):.2e} "
+              f"mean {float(dy.mean()):.2e}/{float(dx.mean()):.2e} px")
+        assert float(dy.max()) <= 3e-3 and float(dx.max()) <= 3e-3
+        assert float(dy.mean()) <= 2e-4 and float(dx.mean()) <= 2e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.uint8])
+def test_low_precision_images_at_staged_sizes(dtype):
+    """16/8-bit images on the default path of large launches (staged kernel + fast
+    coordinates) against the oracle policy: fp32 math on the up-cast input, one
+    rounding at the end; 1 ulp of the output type (truncation flip for uint8)."""
+    if dtype == torch.uint8:
+        base = torch.from_numpy(cases.band_limited_image((2, 3, 512, 1024), "uint8", px=96, py=64))
+    else:
+        base = torch.from_numpy(cases.band_limited_image((2, 3, 512, 1024), "float32", px=96,
+                                                         py=64)).to(dtype)
+    rots = HARD_ROTS[1:3]
+    out = equilib_b200.equi2equi(base.to(DEV), rots)
+    ref = oracle.equi2equi(base, rots, flavour="cuda")
+    assert out.dtype == dtype
+    o, r = out.float().cpu().numpy(), ref.float().numpy()
+    d = np.abs(o - r)
+    if dtype == torch.uint8:
+        assert d.max() <= 1 and np.mean(d == 0) >= 0.97
+    else:
+        ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+        assert d.max() <= ulp * 1.01 + 2e-4
+        assert np.mean(d == 0) >= 0.97
+    exact = equilib_b200.equi2equi(base.to(DEV), rots, fast_coords=False)
+    same = float((exact == out).float().mean())
+    print(f"{dtype}: fast == exact for {same:.5f} of outputs")
+    assert same >= 0.97
+
+
 # ---------------------------------------------------------------------------
 # sampler-only parity: same coordinates in, so only the sampler differs
 # ---------------------------------------------------------------------------
