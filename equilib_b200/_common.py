@@ -152,6 +152,8 @@ def flags_of(dtype: torch.dtype, opt: "Options") -> int:
         flags |= (int(ws) & 3) << _lib.FLAG_WARP_SHAPE_SHIFT
     if os.environ.get("EQUILIB_B200_NO_STAGE") == "1":
         flags |= _lib.FLAG_NO_STAGE
+    if os.environ.get("EQUILIB_B200_NO_TMA") == "1":
+        flags |= _lib.FLAG_NO_TMA
     return flags
 
 

@@ -168,6 +168,72 @@ static bool can_stage(const eqb_remap_desc* d, int px) {
   return (long long)d->batch * d->dst_h * d->dst_w >= (1ll << 18);
 }
 
+// ---- TMA descriptors for the staged kernel ------------------------------------------
+// cuTensorMapEncodeTiled lives in the driver library; it is fetched through the runtime
+// so that this library links against cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) !=
+            cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// Two maps over the source viewed as (W, H, C, B): a wide box for near-upright views and
+// a square one for strongly rotated ones, both within the kernel's shared-memory budget.
+static void setup_tma(const eqb_remap_desc* d, Params& p) {
+  p.use_tma = 0;
+  if (d->flags & EQB_FLAG_NO_TMA) return;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return;
+  const int elt = (int)elt_size(d->dtype);
+  const int per16 = 16 / elt;
+  const long long budget = staged_smem_bytes(elt) / elt / d->channels;  // elements per channel
+  int bw[2], bh[2];
+  bw[0] = 96;
+  bh[0] = (int)(budget / bw[0] < 64 ? budget / bw[0] : 64);
+  int sq = 16;
+  while ((long long)(sq + per16) * (sq + per16) <= budget && sq + per16 <= 96) sq += per16;
+  bw[1] = sq;
+  bh[1] = (int)(budget / sq < 96 ? budget / sq : 96);
+  if (bh[0] < 20 || bh[1] < 20) return;
+  CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                           : d->dtype == EQB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                           : d->dtype == EQB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const bool batched = d->src_stride_b > 0 && d->batch > 1;
+  const cuuint64_t dims[4] = {(cuuint64_t)d->src_w, (cuuint64_t)d->src_h, (cuuint64_t)d->channels,
+                              (cuuint64_t)(batched ? d->batch : 1)};
+  const cuuint64_t cstride = (cuuint64_t)d->src_stride_c * elt;
+  const cuuint64_t strides[3] = {(cuuint64_t)d->src_stride_h * elt,
+                                 d->channels > 1 ? cstride : (cuuint64_t)d->src_stride_h * elt * d->src_h,
+                                 batched ? (cuuint64_t)d->src_stride_b * elt
+                                         : (d->channels > 1 ? cstride : (cuuint64_t)d->src_stride_h * elt * d->src_h) * d->channels};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0 || strides[i] % 16) return;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  for (int m = 0; m < 2; ++m) {
+    const cuuint32_t box[4] = {(cuuint32_t)bw[m], (cuuint32_t)bh[m], (cuuint32_t)d->channels, 1};
+    if (enc(&p.tmaps[m], dt, 4, const_cast<void*>(d->src), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return;
+    p.tma_bw[m] = bw[m];
+    p.tma_bh[m] = bh[m];
+  }
+  p.tma_batched = batched ? 1 : 0;
+  p.use_tma = 1;
+}
+
 // Fast coordinates (exact chain on every 4th pixel + cubic interpolation) are the
 // default for 16- and 8-bit images, opt-in for fp32, and need 4-pixel vector stores.
 static bool can_fast(const eqb_remap_desc* d) {
@@ -186,9 +252,12 @@ static bool can_fast(const eqb_remap_desc* d) {
   return true;
 }
 
-template <int XF> static cudaError_t go(const Params& p, const eqb_remap_desc* d, int px,
+template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int px,
                                         cudaStream_t s) {
-  if (can_stage(d, px)) return launch_staged<XF>(p, d->dtype, can_fast(d), s);
+  if (can_stage(d, px)) {
+    setup_tma(d, p);
+    return launch_staged<XF>(p, d->dtype, can_fast(d), s);
+  }
   return launch_remap<XF>(p, d->mode, d->dtype, px, pick_ws(d), s);
 }
 

@@ -68,9 +68,7 @@ cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px, i
 template <int XF, typename T, int PX, bool FAST, bool CLIP>
 static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   using G = StagedGeom<PX>;
-  // 32 KB of tile per CTA (56 KB for 4-byte pixels): an output tile rotated by any
-  // angle away from the poles fits for C <= 3
-  const int smem = sizeof(T) == 4 ? 56 * 1024 : 32 * 1024;
+  const int smem = staged_smem_bytes((int)sizeof(T));
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(remap_staged_kernel<XF, T, PX, FAST, CLIP>,

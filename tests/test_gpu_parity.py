@@ -226,11 +226,14 @@ def test_staged_and_direct_kernels_agree(dtype, monkeypatch):
             equilib_b200.pers2equi(img, rots, 512, 1024, 90.0, **kw),
             equilib_b200.equi2equi(img[:, :, :, :1000], rots, height=500, width=1002, **kw),
         ]
-    staged = run_all()
+    staged = run_all()                      # TMA box loads
+    monkeypatch.setenv("EQUILIB_B200_NO_TMA", "1")
+    staged_cp_async = run_all()             # 16-byte cp.async row chunks
     monkeypatch.setenv("EQUILIB_B200_NO_STAGE", "1")
-    direct = run_all()
-    for a, b in zip(staged, direct):
-        assert torch.equal(a, b)
+    direct = run_all()                      # global gathers
+    for a, b, c in zip(staged, staged_cp_async, direct):
+        assert torch.equal(a, c)
+        assert torch.equal(b, c)
 
 
 HARD_ROTS = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}, {"roll": 0.3, "pitch": -0.4, "yaw": 1.1},
