@@ -188,8 +188,9 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// Two maps over the source viewed as (W, H, C, B): a wide box for near-upright views and
-// a square one for strongly rotated ones, both within the kernel's shared-memory budget.
+// Tensor maps over the source viewed as (W, H, C, B): a wide box for near-upright views,
+// a square one for views rotated by 45 degrees and one in between, all within the
+// kernel's shared-memory budget.
 static void setup_tma(const eqb_remap_desc* d, Params& p) {
   p.use_tma = 0;
   if (d->flags & EQB_FLAG_NO_TMA) return;
@@ -198,14 +199,17 @@ static void setup_tma(const eqb_remap_desc* d, Params& p) {
   const int elt = (int)elt_size(d->dtype);
   const int per16 = 16 / elt;
   const long long budget = staged_smem_bytes(elt) / elt / d->channels;  // elements per channel
-  int bw[2], bh[2];
-  bw[0] = 96;
-  bh[0] = (int)(budget / bw[0] < 64 ? budget / bw[0] : 64);
+  // box shapes within the budget: wide / intermediate / square, widths multiples of 16 B
+  int bw[kTmaBoxes], bh[kTmaBoxes];
+  auto rows = [&](int w) { long long r = budget / w; return (int)(r < 128 ? r : 128); };
   int sq = 16;
   while ((long long)(sq + per16) * (sq + per16) <= budget && sq + per16 <= 96) sq += per16;
-  bw[1] = sq;
-  bh[1] = (int)(budget / sq < 96 ? budget / sq : 96);
-  if (bh[0] < 20 || bh[1] < 20) return;
+  bw[0] = 96;
+  bw[2] = sq;
+  bw[1] = ((bw[0] + bw[2]) / 2 + per16 - 1) / per16 * per16;
+  bw[3] = 192;  // high source latitudes stretch the footprint along x by 1/cos(lat)
+  for (int m = 0; m < kTmaBoxes; ++m) bh[m] = rows(bw[m]);
+  if (bh[0] < 20 || bh[2] < 20 || bh[3] < 20) return;
   CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                            : d->dtype == EQB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                            : d->dtype == EQB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -221,7 +225,7 @@ static void setup_tma(const eqb_remap_desc* d, Params& p) {
   for (int i = 0; i < 3; ++i)
     if (strides[i] == 0 || strides[i] % 16) return;
   const cuuint32_t ones[4] = {1, 1, 1, 1};
-  for (int m = 0; m < 2; ++m) {
+  for (int m = 0; m < kTmaBoxes; ++m) {
     const cuuint32_t box[4] = {(cuuint32_t)bw[m], (cuuint32_t)bh[m], (cuuint32_t)d->channels, 1};
     if (enc(&p.tmaps[m], dt, 4, const_cast<void*>(d->src), dims, strides, box, ones,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
