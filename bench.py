@@ -87,55 +87,74 @@ def synth_frames(wl, device, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / power / throttle reasons sampled every few ms DURING the timed region
+    (NVML from a thread; the timed region is tens of ms, too short for `nvidia-smi -lms`)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.004):
         self.index = index
-        self.proc = None
-        self.path = None
+        self.period = period_s
+        self.samples = []
+        self._stop = False
+        self._thread = None
+        self._nvml = None
 
     def start(self):
+        import threading
+
         try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
         except Exception:
-            self.proc = None
+            self._nvml = None
+            return
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def _loop(self):
+        n = self._nvml
+        while not self._stop:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                pw = 0.0
+                if len(self.samples) % 4 == 0:  # power is the slow query
+                    pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                self.samples.append((sm, reasons, pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        n = self._nvml
+        if n is None or not self.samples:
             return out
         try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            try:
-                self.proc.kill()
-            except Exception:
-                pass
-        try:
-            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
-            os.unlink(self.path)
-            sm = [float(r[0]) for r in rows if len(r) >= 7]
-            if sm:
-                out["sm_mhz"] = statistics.median(sm)
-                out["sm_max_mhz"] = float(rows[0][1])
-                out["power_w_max"] = max(float(r[2]) for r in rows if len(r) >= 7)
-                out["samples"] = len(sm)
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for j, n in enumerate(names):
-                    if any("Active" in r[3 + j] and "Not" not in r[3 + j] for r in rows if len(r) >= 7):
-                        out["reasons"].append(n)
+            out["sm_max_mhz"] = float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
         except Exception:
             pass
+        out["sm_mhz"] = float(statistics.median(s[0] for s in self.samples))
+        out["power_w_max"] = max(s[2] for s in self.samples)
+        out["samples"] = len(self.samples)
+        bits = 0
+        for s_ in self.samples:
+            bits |= int(s_[1])
+        names = {
+            "hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        out["reasons"] = [k for k, v in names.items() if bits & int(v)]
         return out
 
 
@@ -197,8 +216,8 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="e2e_4k_bf16_b32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -252,8 +271,7 @@ def main():
         out = op(src, rots)
     barrier()
 
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ
-                           else local_rank)
+    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = _lib.launch_count()
@@ -276,24 +294,22 @@ def main():
     px_per_step = b * h * w * world
     value = px_per_step / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end: pinned host frames in, pinned host frames out, per step
+    # ---- end to end: pinned host frames in, pinned host frames out, per step, through
+    # the public streaming helper (H2D | remap | D2H overlapped on three streams)
     e2e = None
     if not args.no_e2e:
+        from equilib_b200.pipeline import HostPipeline
+
         hin = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
         hin.copy_(src)
         hout = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        pipe = HostPipeline(op, chunk=4, device=dev)
         steps2 = max(2, min(args.steps, 5))
-
-        def e2e_step():
-            x = hin.to(dev, non_blocking=True)
-            y = op(x, rots)
-            hout.copy_(y, non_blocking=True)
-
-        e2e_step()
+        pipe(hin, rots, out=hout)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps2):
-            e2e_step()
+            pipe(hin, rots, out=hout)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t2 = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -303,7 +319,8 @@ def main():
                "h2d_bytes_per_step": hin.numel() * hin.element_size(),
                "d2h_bytes_per_step": hout.numel() * hout.element_size(),
                "steps": steps2,
-               "path": "pinned host -> H2D -> equilib_b200.Equi2Equi -> D2H -> pinned host"}
+               "path": "pinned host -> equilib_b200.pipeline.HostPipeline(Equi2Equi, chunk=4): "
+                       "H2D | remap | D2H on three streams -> pinned host"}
         del hin, hout
 
     if rank != 0:
@@ -335,7 +352,10 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": "eqb::remap_kernel<EQUI2EQUI,BILINEAR>"},
+                     "kernel": ("eqb::remap_kernel<EQUI2EQUI,BILINEAR,float> (direct gather)"
+                                if wl["dtype"] == "float32" else
+                                "eqb::remap_staged_kernel<EQUI2EQUI,%s,PX=4,FAST> (TMA-staged)"
+                                % wl["dtype"])},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
     }

@@ -578,3 +578,20 @@ def test_launches_are_counted_and_on_current_stream():
     assert _lib.launch_count() == n0 + 1
     b = equilib_b200.equi2equi(img, rots)
     assert torch.equal(a, b)
+
+
+def test_host_pipeline_matches_direct_call():
+    from equilib_b200.pipeline import HostPipeline
+
+    frames = torch.from_numpy(cases.noise_image((10, 3, 64, 128), "uint8", 77)).pin_memory()
+    rots = cases.rotation_sweep(13)[3:]
+    op = equilib_b200.Equi2Equi(mode="bilinear")
+    want = op(frames.to(DEV), rots).cpu()
+    pipe = HostPipeline(op, chunk=4)
+    got = pipe(frames, rots)
+    torch.cuda.synchronize()
+    assert got.is_pinned() and torch.equal(got, want)
+    out = torch.empty_like(frames).pin_memory()
+    assert pipe(frames, rots, out=out) is out
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)

@@ -143,3 +143,11 @@ def test_product_never_imports_oracle_or_grid_sample():
             code = re.sub(r"#.*", "", code)
             assert "oracle" not in code, fn
             assert "F.grid_sample" not in code and "functional" not in code, fn
+
+
+def test_host_pipeline_chunking():
+    from equilib_b200.pipeline import HostPipeline
+
+    assert [list(r) for r in HostPipeline.chunks(10, 4)] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+    assert [list(r) for r in HostPipeline.chunks(3, 4)] == [[0, 1, 2]]
+    assert HostPipeline.chunks(0, 4) == []
