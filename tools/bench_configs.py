@@ -1,0 +1,139 @@
+#!/usr/bin/env python3
+"""Device-resident timing of every BASELINE.json config (CUDA events, one GPU).
+
+    python tools/bench_configs.py > gpurun_out/configs.jsonl
+
+Not the graded bench (that is bench.py on configs[1]); these lines document the other
+configs in DESIGN.md.  Mpix/s counts output pixels; GB/s counts algorithmic bytes
+(whole source read once + output written once; for equi2pers the source term is the
+upper bound "whole frame").
+"""
+
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import equilib_b200  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+
+
+def rots(n):
+    return [{"roll": 0.01 * i, "pitch": 0.4 * math.sin(i), "yaw": 0.05 * i} for i in range(n)]
+
+
+def timed(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def frames(b, c, h, w, dtype):
+    if dtype == torch.uint8:
+        return torch.randint(0, 256, (b, c, h, w), dtype=torch.uint8, device=DEV)
+    return torch.rand((b, c, h, w), device=DEV).to(dtype)
+
+
+def report(name, ms, out_px, alg_bytes, **kw):
+    rec = {"config": name, "ms": round(ms, 4), "mpix_s": round(out_px / ms / 1e3, 1),
+           "alg_gb_s": round(alg_bytes / ms / 1e6, 1),
+           "frac_hbm_6553": round(alg_bytes / ms / 1e6 / 6553.3, 4)}
+    rec.update(kw)
+    print(json.dumps(rec), flush=True)
+
+
+def main():
+    # config 1: equi2pers bilinear, batch 1, 3x2048x4096 fp32 -> 480x640, fov 90
+    equi = frames(1, 3, 2048, 4096, torch.float32)
+    rot = {"roll": 0.1, "pitch": 0.3, "yaw": -0.5}
+    op = equilib_b200.Equi2Pers(480, 640, 90.0)
+    ms = timed(lambda: op(equi[0], rot), steps=50, warmup=5)
+    report("1: equi2pers fp32 4K -> 480x640 (device time per call, back to back)", ms, 480 * 640,
+           480 * 640 * 3 * 4 * 2, note="latency-bound; includes host dispatch when it dominates")
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        op(equi[0], rot)
+    torch.cuda.synchronize()
+    report("1: same, wall clock per call incl. python + custom-op dispatch",
+           (time.perf_counter() - t0) / 200 * 1e3, 480 * 640, 480 * 640 * 3 * 4 * 2)
+    del equi
+
+    # config 2 family: equi2equi batch 32 bf16 / fp32 / uint8, three modes
+    for dtype, b in ((torch.bfloat16, 32), (torch.float32, 16), (torch.uint8, 32)):
+        src = frames(b, 3, 2048, 4096, dtype)
+        r = rots(b)
+        for mode in ("nearest", "bilinear", "bicubic"):
+            ms = timed(lambda: equilib_b200.equi2equi(src, r, mode=mode))
+            px = b * 2048 * 4096
+            report(f"2: equi2equi {str(dtype)[6:]} b{b} 4K {mode}", ms, px,
+                   2 * px * 3 * src.element_size())
+        if dtype == torch.float32:
+            ms = timed(lambda: equilib_b200.equi2equi(src, r, fast_coords=True))
+            report("2: equi2equi float32 b16 4K bilinear fast_coords=True (opt-in)", ms,
+                   b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 4)
+        del src
+
+    # config 3: equi2cube + cube2equi, batch 16, w_face 1024, fp32 and uint8
+    for dtype in (torch.float32, torch.uint8):
+        equi = frames(16, 3, 2048, 4096, dtype)
+        r = rots(16)
+        es = equi.element_size()
+        for fmt in ("dice", "horizon", "dict"):
+            for mode in ("nearest", "bilinear"):
+                ms = timed(lambda: equilib_b200.equi2cube(equi, r, 1024, fmt, mode=mode), steps=5)
+                out_px = 16 * 6 * 1024 * 1024
+                extra = 16 * 6 * 1024 * 1024 * 3 * es if fmt == "dice" else 0
+                report(f"3: equi2cube {str(dtype)[6:]} b16 4K -> w1024 {fmt} {mode}", ms, out_px,
+                       16 * 3 * (2048 * 4096 + 6 * 1024 * 1024) * es + extra)
+            cube = equilib_b200.equi2cube(equi, r, 1024, fmt, mode="bilinear")
+            for mode in ("nearest", "bilinear"):
+                ms = timed(lambda: equilib_b200.cube2equi(cube, fmt, 2048, 4096, mode=mode), steps=5)
+                report(f"3: cube2equi {str(dtype)[6:]} b16 w1024 {fmt} -> 4K {mode}", ms,
+                       16 * 2048 * 4096, 16 * 3 * (2048 * 4096 + 6 * 1024 * 1024) * es)
+            del cube
+        del equi
+
+    # config 4 (per GPU share: 8 frames of 3x4096x8192 uint8, bicubic)
+    equi = frames(8, 3, 4096, 8192, torch.uint8)
+    r = rots(8)
+    ms = timed(lambda: equilib_b200.equi2pers(equi, r, 1080, 1920, 90.0, mode="bicubic"), steps=5)
+    report("4: equi2pers uint8 bicubic 8K -> 1080x1920, 8 frames", ms, 8 * 1080 * 1920,
+           8 * 1080 * 1920 * 3 * 2, note="alg bytes = write + equal-size footprint lower bound")
+    pers = frames(8, 3, 1080, 1920, torch.uint8)
+    ms = timed(lambda: equilib_b200.pers2equi(pers, r, 4096, 8192, 90.0, mode="bicubic"), steps=5)
+    report("4: pers2equi uint8 bicubic 1080x1920 -> 8K, 8 frames", ms, 8 * 4096 * 8192,
+           8 * 3 * (4096 * 8192 + 1080 * 1920))
+    del equi, pers
+
+    # config 5: one fp16 equirect x 256 rotations -> 3x1024x1024 (stride-0 batch)
+    equi = frames(1, 3, 2048, 4096, torch.float16).expand(256, -1, -1, -1)
+    r = [{"roll": 0.0, "pitch": 0.5 * math.sin(0.1 * i), "yaw": 2 * math.pi * i / 256}
+         for i in range(256)]
+    ms = timed(lambda: equilib_b200.equi2pers(equi, r, 1024, 1024, 90.0), steps=5)
+    report("5: equi2pers fp16 1 x 256 views -> 1024x1024 (expanded batch)", ms, 256 * 1024 * 1024,
+           256 * 1024 * 1024 * 3 * 2 + 3 * 2048 * 4096 * 2)
+    r2 = [dict(x, roll=0.001) for x in r]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    equilib_b200.equi2pers(equi, r2, 1024, 1024, 90.0)
+    torch.cuda.synchronize()
+    report("5: same, first call with NEW rotations (host matrix prep + upload + launch), wall",
+           (time.perf_counter() - t0) * 1e3, 256 * 1024 * 1024,
+           256 * 1024 * 1024 * 3 * 2 + 3 * 2048 * 4096 * 2)
+
+
+if __name__ == "__main__":
+    main()
