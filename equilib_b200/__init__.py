@@ -10,7 +10,7 @@ never called and there is no CPU fallback.
 from .cube2equi import Cube2Equi, cube2equi
 from .equi2cube import Equi2Cube, equi2cube
 from .equi2equi import Equi2Equi, equi2equi
-from .equi2pers import Equi2Pers, equi2pers
+from .equi2pers import Equi2Pers, equi2pers, get_bounding_fov
 from .grid_sample import grid_sample
 from .pers2equi import Pers2Equi, pers2equi
 
@@ -28,4 +28,5 @@ __all__ = [
     "equi2pers",
     "pers2equi",
     "grid_sample",
+    "get_bounding_fov",
 ]

@@ -69,12 +69,11 @@ template <int XF, typename T, int PX, bool FAST, bool CLIP>
 static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   using G = StagedGeom<PX>;
   const int smem = staged_smem_bytes((int)sizeof(T));
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in is per device (a process may drive several GPUs): set it on every launch
+  // that needs more than the 48 KB default
+  if (smem > 48 * 1024)
     cudaFuncSetAttribute(remap_staged_kernel<XF, T, PX, FAST, CLIP>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
   p.smem_elems = smem / (int)sizeof(T);
   const long long tiles_x = (p.dw + G::tile_w - 1) / G::tile_w;
   const long long tiles_y = (p.dh + G::tile_h - 1) / G::tile_h;

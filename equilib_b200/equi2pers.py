@@ -6,10 +6,12 @@ from typing import Dict, List, Union
 
 import torch
 
-from . import _common as K
-from . import _lib, _prep
+import numpy as np
 
-__all__ = ["Equi2Pers", "equi2pers"]
+from . import _common as K
+from . import _lib, _ops, _prep
+
+__all__ = ["Equi2Pers", "equi2pers", "get_bounding_fov"]
 
 Rot = Union[Dict[str, float], List[Dict[str, float]]]
 
@@ -52,6 +54,18 @@ class Equi2Pers(object):
             mode=self.mode,
             clip_output=self.clip_output,
             **kwargs,
+        )
+
+
+    def get_bounding_fov(self, equi: torch.Tensor, rots: Rot) -> np.ndarray:
+        return get_bounding_fov(
+            equi=equi,
+            rots=rots,
+            height=self.height,
+            width=self.width,
+            fov_x=self.fov_x,
+            skew=self.skew,
+            z_down=self.z_down,
         )
 
 
@@ -99,4 +113,44 @@ def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
         src_hw=(h_equi, w_equi), dst_hw=(height, width),
         src_strides=equi.stride()[:3], dst_strides=out.stride()[:3], mats=mats, clip=clip,
     )
+    return out
+
+
+def get_bounding_fov(
+    equi: torch.Tensor,
+    rots: Rot,
+    height: int,
+    width: int,
+    fov_x: float,
+    skew: float = 0.0,
+    z_down: bool = False,
+) -> np.ndarray:
+    """Perimeter of the perspective view in equirectangular pixel coordinates,
+    (B, 2*width + 2*(height-2), 2) int64 as (row, col), clockwise from the top-left
+    corner -- drop-in for equilib/equi2pers/base.py:166-226 / torch.py:247-351.
+
+    The coordinates come from the same device chain the remap uses
+    (``eqb_remap_coords``); only the perimeter is copied back to the host."""
+    K.require_cuda_tensor(equi, "equi")
+    equi, rots, is_single = K.normalise_single(equi, rots)
+    equi = K.check_image(equi, "equi")
+    assert len(equi) == len(rots), (
+        f"ERR: length of equi and rot differs: {len(equi)} vs {len(rots)}"
+    )
+    bs, _, h_equi, w_equi = equi.shape
+    dev = equi.device
+    mats = _prep.mats_for("equi2pers", rots, z_down, dev,
+                          (int(height), int(width), float(fov_x), float(skew)))
+    grid = torch.empty((bs, 2, height, width), dtype=torch.float32, device=dev)
+    _ops.coords(grid, mats, None, None, None, None, _lib.EQUI2PERS, bs, h_equi, w_equi,
+                height, width)
+    top = grid[:, :, 0, :]
+    right = grid[:, :, 1:, width - 1]
+    bottom = grid[:, :, height - 1, 1:width - 1].flip(-1)
+    left = grid[:, :, 1:, 0].flip(-1)
+    bboxs = torch.cat([top, right, bottom, left], dim=-1).permute(0, 2, 1)
+    assert bboxs.shape[1] == width * 2 + (height - 2) * 2
+    out = np.rint(bboxs.cpu().numpy()).astype(np.int64)
+    if is_single:
+        out = out.squeeze(0)
     return out

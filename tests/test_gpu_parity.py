@@ -595,3 +595,25 @@ def test_host_pipeline_matches_direct_call():
     assert pipe(frames, rots, out=out) is out
     torch.cuda.synchronize()
     assert torch.equal(out, want)
+
+
+def test_get_bounding_fov_matches_oracle_perimeter():
+    """equilib/equi2pers/torch.py:247-351: rounded (row, col) of the view's perimeter."""
+    h, w, H, W = 48, 64, 256, 512
+    rots = cases.rotation_sweep(6)[3:]
+    equi = torch.zeros((3, 3, H, W), device=DEV)
+    got = equilib_b200.Equi2Pers(h, w, 90.0).get_bounding_fov(equi, rots)
+    assert got.shape == (3, 2 * w + 2 * (h - 2), 2) and got.dtype == np.int64
+    uj, ui = O.equi2pers_coords(rots, False, h, w, 90.0, 0.0, H, W)
+    g = torch.stack([uj, ui], dim=1)  # (B, 2, h, w)
+    per = []
+    per += [g[:, :, 0, x] for x in range(w)]
+    per += [g[:, :, y, w - 1] for y in range(1, h)]
+    per += [g[:, :, h - 1, x] for x in range(w - 2, 0, -1)]
+    per += [g[:, :, y, 0] for y in range(h - 1, 0, -1)]
+    want = np.rint(torch.stack(per, dim=1).numpy()).astype(np.int64)
+    d = np.abs(got - want)
+    d[..., 1] = np.minimum(d[..., 1], W - d[..., 1])  # seam
+    assert d.max() <= 1 and np.mean(d == 0) >= 0.995
+    one = equilib_b200.get_bounding_fov(equi[0], rots[0], h, w, 90.0)
+    assert one.shape == (2 * w + 2 * (h - 2), 2) and np.array_equal(one, got[0])
