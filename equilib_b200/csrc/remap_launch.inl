@@ -65,47 +65,51 @@ cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px, i
 }
 
 #if EQB_XF != 3  // not EQB_CUBE2EQUI (enum values are invisible to the preprocessor)
-template <int XF, typename T, int PX, bool FAST, bool CLIP>
+template <int XF, int MODE, typename T, int PX, bool FAST, bool CLIP>
 static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   using G = StagedGeom<PX>;
   const int smem = staged_smem_bytes((int)sizeof(T));
   // the opt-in is per device (a process may drive several GPUs): set it on every launch
   // that needs more than the 48 KB default
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(remap_staged_kernel<XF, T, PX, FAST, CLIP>,
+    cudaFuncSetAttribute(remap_staged_kernel<XF, MODE, T, PX, FAST, CLIP>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   p.smem_elems = smem / (int)sizeof(T);
   const long long tiles_x = (p.dw + G::tile_w - 1) / G::tile_w;
   const long long tiles_y = (p.dh + G::tile_h - 1) / G::tile_h;
   p.iters = tiles_x * tiles_y * p.B >= 148ll * 64 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
-  remap_staged_kernel<XF, T, PX, FAST, CLIP><<<grid, kWarps * 32, smem, stream>>>(p);
+  remap_staged_kernel<XF, MODE, T, PX, FAST, CLIP><<<grid, kWarps * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <int XF, typename T, int PX, bool FAST>
+template <int XF, int MODE, typename T, int PX, bool FAST>
 static cudaError_t launch_staged_one(const Params& p, cudaStream_t stream) {
-  if (p.clip) return launch_staged_clip<XF, T, PX, FAST, true>(p, stream);
-  return launch_staged_clip<XF, T, PX, FAST, false>(p, stream);
+  if (p.clip) return launch_staged_clip<XF, MODE, T, PX, FAST, true>(p, stream);
+  return launch_staged_clip<XF, MODE, T, PX, FAST, false>(p, stream);
 }
 
+// bilinear: PX per dtype, or the 4-pixel fast-coordinate variant; bicubic: exact
+// coordinates, 2 pixels per lane (8 cubic weights per pixel are live in the blend)
 template <int XF, typename T, int PX>
-static cudaError_t launch_staged_t(const Params& p, bool fast, cudaStream_t stream) {
+static cudaError_t launch_staged_t(const Params& p, int mode, bool fast, cudaStream_t stream) {
+  if (mode == EQB_BICUBIC) return launch_staged_one<XF, EQB_BICUBIC, T, 2, false>(p, stream);
 #if EQB_XF <= 2  // transforms with a transcendental chain have a fast-coordinate variant
-  if (fast) return launch_staged_one<XF, T, 4, true>(p, stream);
+  if (fast) return launch_staged_one<XF, EQB_BILINEAR, T, 4, true>(p, stream);
 #endif
-  return launch_staged_one<XF, T, PX, false>(p, stream);
+  return launch_staged_one<XF, EQB_BILINEAR, T, PX, false>(p, stream);
 }
 #endif
 
 template <>
-cudaError_t launch_staged<EQB_XF>(const Params& p, int dtype, bool fast, cudaStream_t stream) {
+cudaError_t launch_staged<EQB_XF>(const Params& p, int mode, int dtype, bool fast,
+                                  cudaStream_t stream) {
 #if EQB_XF != 3
   switch (dtype) {
-    case EQB_U8: return launch_staged_t<EQB_XF, uint8_t, 4>(p, fast, stream);
-    case EQB_F16: return launch_staged_t<EQB_XF, __half, 2>(p, fast, stream);
-    case EQB_BF16: return launch_staged_t<EQB_XF, __nv_bfloat16, 2>(p, fast, stream);
-    case EQB_F32: return launch_staged_t<EQB_XF, float, 2>(p, fast, stream);
+    case EQB_U8: return launch_staged_t<EQB_XF, uint8_t, 4>(p, mode, fast, stream);
+    case EQB_F16: return launch_staged_t<EQB_XF, __half, 2>(p, mode, fast, stream);
+    case EQB_BF16: return launch_staged_t<EQB_XF, __nv_bfloat16, 2>(p, mode, fast, stream);
+    case EQB_F32: return launch_staged_t<EQB_XF, float, 2>(p, mode, fast, stream);
   }
 #endif
   return cudaErrorInvalidValue;

@@ -225,6 +225,11 @@ def test_staged_and_direct_kernels_agree(dtype, monkeypatch):
             equilib_b200.equi2cube(img, rots, 256, "horizon", **kw),
             equilib_b200.pers2equi(img, rots, 512, 1024, 90.0, **kw),
             equilib_b200.equi2equi(img[:, :, :, :1000], rots, height=500, width=1002, **kw),
+            # bicubic: staged tiles read the 4x4 taps from the box, border tiles reflect
+            equilib_b200.equi2equi(img, rots, mode="bicubic", **kw),
+            equilib_b200.equi2pers(img, rots, 480, 640, 100.0, mode="bicubic", **kw),
+            equilib_b200.equi2cube(img, rots, 256, "dice", mode="bicubic", clip_output=False, **kw),
+            equilib_b200.pers2equi(img, rots, 512, 1024, 90.0, mode="bicubic", **kw),
         ]
     staged = run_all()                      # TMA box loads
     monkeypatch.setenv("EQUILIB_B200_NO_TMA", "1")
