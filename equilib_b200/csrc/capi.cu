@@ -31,8 +31,9 @@ static size_t elt_size(int dtype) {
   return 0;
 }
 
-static int vec_px(int dtype, int mode) {
+static int vec_px(int dtype, int mode, int transform) {
   if (mode == EQB_BICUBIC) return 1;
+  if (transform == EQB_CUBE2EQUI && mode == EQB_BILINEAR) return 2;  // see launch_px
   return dtype == EQB_U8 ? 4 : 2;
 }
 
@@ -130,7 +131,7 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
 // Widest store the destination layout allows: every row start of every plane (and
 // cell) must be aligned to PX elements.
 static int pick_px(const eqb_remap_desc* d) {
-  const int v = vec_px(d->dtype, d->mode);
+  const int v = vec_px(d->dtype, d->mode, d->transform);
   const size_t bytes = v * elt_size(d->dtype);
   if (reinterpret_cast<uintptr_t>(d->dst) % bytes) return 1;
   if (d->dst_stride_b % v || d->dst_stride_c % v || d->dst_stride_h % v) return 1;
@@ -167,15 +168,17 @@ static bool dst_vector_ok(const eqb_remap_desc* d, int v) {
 
 static bool can_stage(const eqb_remap_desc* d) {
   if (d->flags & EQB_FLAG_NO_STAGE) return false;
-  if (d->transform == EQB_CUBE2EQUI) return false;
+  if (d->transform == EQB_CUBE2EQUI) {
+    // only a true horizon strip is one plain image the box loads can address; its
+    // cross-face tap bleed is then simply what the memory holds
+    if (d->face_ptrs || d->src_stride_h < 6ll * d->w_face) return false;
+    for (int i = 0; i < 6; ++i)
+      if (d->cell_offset[i] != (long long)i * d->w_face) return false;
+  }
   // pers2equi: most of the output lies outside the field of view and is a plain fill in
   // the direct kernel (no taps, no tile synchronisation): 1.7 ms vs 3.4 ms for 8 x 8K
   if (d->transform == EQB_PERS2EQUI) return false;
   if (d->mode != EQB_BILINEAR && d->mode != EQB_BICUBIC) return false;
-  // fp32 bilinear with the exact coordinate chain is faster on the direct-gather kernel
-  // (4-byte gathers touch the same number of lines, and 80 registers leave 3 CTAs per SM)
-  if (d->mode == EQB_BILINEAR && d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS))
-    return false;
   // store width of the staged kernel: 2 pixels (bicubic, 16/32-bit bilinear), 4 (uint8)
   const int v = d->mode == EQB_BICUBIC ? 2 : (d->dtype == EQB_U8 ? 4 : 2);
   if (!dst_vector_ok(d, v)) return false;

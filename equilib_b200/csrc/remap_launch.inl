@@ -39,7 +39,10 @@ static cudaError_t launch_ws(const Params& p, int ws, cudaStream_t stream) {
 template <int XF, int MODE, typename T>
 static cudaError_t launch_px(const Params& p, int px, int ws, cudaStream_t stream) {
   if (px == 1) return launch_ws<XF, MODE, T, 1>(p, ws, stream);
-  return launch_ws<XF, MODE, T, VecPX<T, MODE>::value>(p, ws, stream);
+  // cube2equi carries one offset and face id per tap: 4 uint8 pixels per thread spill
+  constexpr int V = (XF == EQB_CUBE2EQUI && MODE == EQB_BILINEAR && sizeof(T) == 1)
+                        ? 2 : VecPX<T, MODE>::value;
+  return launch_ws<XF, MODE, T, V>(p, ws, stream);
 }
 
 template <int XF, int MODE>
@@ -64,7 +67,6 @@ cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px, i
   return cudaErrorInvalidValue;
 }
 
-#if EQB_XF != 3  // not EQB_CUBE2EQUI (enum values are invisible to the preprocessor)
 template <int XF, int MODE, typename T, int PX, bool FAST, bool CLIP>
 static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   using G = StagedGeom<PX>;
@@ -95,23 +97,21 @@ template <int XF, typename T, int PX>
 static cudaError_t launch_staged_t(const Params& p, int mode, bool fast, cudaStream_t stream) {
   if (mode == EQB_BICUBIC) return launch_staged_one<XF, EQB_BICUBIC, T, 2, false>(p, stream);
 #if EQB_XF <= 2  // transforms with a transcendental chain have a fast-coordinate variant
+         // (enum values are invisible to the preprocessor: 0..2 = equi2equi/pers/cube)
   if (fast) return launch_staged_one<XF, EQB_BILINEAR, T, 4, true>(p, stream);
 #endif
   return launch_staged_one<XF, EQB_BILINEAR, T, PX, false>(p, stream);
 }
-#endif
 
 template <>
 cudaError_t launch_staged<EQB_XF>(const Params& p, int mode, int dtype, bool fast,
                                   cudaStream_t stream) {
-#if EQB_XF != 3
   switch (dtype) {
     case EQB_U8: return launch_staged_t<EQB_XF, uint8_t, 4>(p, mode, fast, stream);
     case EQB_F16: return launch_staged_t<EQB_XF, __half, 2>(p, mode, fast, stream);
     case EQB_BF16: return launch_staged_t<EQB_XF, __nv_bfloat16, 2>(p, mode, fast, stream);
     case EQB_F32: return launch_staged_t<EQB_XF, float, 2>(p, mode, fast, stream);
   }
-#endif
   return cudaErrorInvalidValue;
 }
 

@@ -230,6 +230,10 @@ def test_staged_and_direct_kernels_agree(dtype, monkeypatch):
             equilib_b200.equi2pers(img, rots, 480, 640, 100.0, mode="bicubic", **kw),
             equilib_b200.equi2cube(img, rots, 256, "dice", mode="bicubic", clip_output=False, **kw),
             equilib_b200.pers2equi(img, rots, 512, 1024, 90.0, mode="bicubic", **kw),
+            # cube2equi from a true horizon strip is a plain image for the box loads
+            equilib_b200.cube2equi(img[:, :, :128, :768].contiguous(), "horizon", 512, 1024),
+            equilib_b200.cube2equi(img[:, :, :128, :768].contiguous(), "horizon", 512, 1024,
+                                   mode="bicubic", clip_output=False),
         ]
     staged = run_all()                      # TMA box loads
     monkeypatch.setenv("EQUILIB_B200_NO_TMA", "1")
