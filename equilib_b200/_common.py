@@ -156,6 +156,8 @@ def flags_of(dtype: torch.dtype, opt: "Options") -> int:
         flags |= _lib.FLAG_NO_TMA
     if os.environ.get("EQUILIB_B200_FORCE_STAGE") == "1":
         flags |= _lib.FLAG_FORCE_STAGE
+    if os.environ.get("EQUILIB_B200_NO_LEAN") == "1":
+        flags |= _lib.FLAG_NO_LEAN
     return flags
 
 

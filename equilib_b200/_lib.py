@@ -27,6 +27,7 @@ FLAG_EXACT_COORDS = 16
 FLAG_FAST_COORDS = 32
 FLAG_NO_TMA = 64
 FLAG_FORCE_STAGE = 128
+FLAG_NO_LEAN = 1024
 FLAG_WARP_SHAPE_SHIFT = 8
 
 MODES = {"nearest": NEAREST, "bilinear": BILINEAR, "bicubic": BICUBIC}

@@ -219,19 +219,13 @@ static void setup_tma(const eqb_remap_desc* d, Params& p) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return;
   const int elt = (int)elt_size(d->dtype);
-  const int per16 = 16 / elt;
-  const long long budget = staged_smem_bytes(elt) / elt / d->channels;  // elements per channel
-  // box shapes within the budget: wide / intermediate / square, widths multiples of 16 B
+  // box shapes: the compile-time table the kernels are specialised on
   int bw[kTmaBoxes], bh[kTmaBoxes];
-  auto rows = [&](int w) { long long r = budget / w; return (int)(r < 128 ? r : 128); };
-  int sq = 16;
-  while ((long long)(sq + per16) * (sq + per16) <= budget && sq + per16 <= 96) sq += per16;
-  bw[0] = 96;
-  bw[2] = sq;
-  bw[1] = ((bw[0] + bw[2]) / 2 + per16 - 1) / per16 * per16;
-  bw[3] = 192;  // high source latitudes stretch the footprint along x by 1/cos(lat)
-  for (int m = 0; m < kTmaBoxes; ++m) bh[m] = rows(bw[m]);
-  if (bh[0] < 20 || bh[2] < 20 || bh[3] < 20) return;
+  for (int m = 0; m < kTmaBoxes; ++m) {
+    bw[m] = box_w(elt, m);
+    bh[m] = box_h(elt, d->channels, m);
+  }
+  if (bh[3] < 20) return;  // (more than 4 channels of 4-byte pixels)
   CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                            : d->dtype == EQB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                            : d->dtype == EQB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
@@ -256,6 +250,7 @@ static void setup_tma(const eqb_remap_desc* d, Params& p) {
     p.tma_bw[m] = bw[m];
     p.tma_bh[m] = bh[m];
   }
+  for (int m = kTmaBoxes; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
   p.tma_batched = batched ? 1 : 0;
   p.use_tma = 1;
 }

@@ -67,6 +67,10 @@ cudaError_t launch_remap<EQB_XF>(const Params& p, int mode, int dtype, int px, i
   return cudaErrorInvalidValue;
 }
 
+// (the lean kernel is not instantiated for 4-byte pixels)
+template <typename T> struct LeanType { using type = T; };
+template <> struct LeanType<float> { using type = __nv_bfloat16; };
+
 template <int XF, int MODE, typename T, int PX, bool FAST, bool CLIP>
 static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   using G = StagedGeom<PX>;
@@ -85,6 +89,20 @@ static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// Lean variant of <BILINEAR, PX 4, FAST, no clip> for three channels of 1- or 2-byte pixels
+// through TMA (the headline case).
+template <int XF, typename T>
+static cudaError_t launch_lean(Params p, cudaStream_t stream) {
+  using G = StagedGeom<4>;
+  const int smem = staged_smem_bytes((int)sizeof(T));
+  const long long tiles_x = (p.dw + G::tile_w - 1) / G::tile_w;
+  const long long tiles_y = (p.dh + G::tile_h - 1) / G::tile_h;
+  p.iters = tiles_x * tiles_y * p.B >= 148ll * 64 ? 4 : 1;
+  const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
+  remap_lean_kernel<XF, T><<<grid, kWarps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 template <int XF, int MODE, typename T, int PX, bool FAST>
 static cudaError_t launch_staged_one(const Params& p, cudaStream_t stream) {
   if (p.clip) return launch_staged_clip<XF, MODE, T, PX, FAST, true>(p, stream);
@@ -98,7 +116,11 @@ static cudaError_t launch_staged_t(const Params& p, int mode, bool fast, cudaStr
   if (mode == EQB_BICUBIC) return launch_staged_one<XF, EQB_BICUBIC, T, 2, false>(p, stream);
 #if EQB_XF <= 2  // transforms with a transcendental chain have a fast-coordinate variant
          // (enum values are invisible to the preprocessor: 0..2 = equi2equi/pers/cube)
-  if (fast) return launch_staged_one<XF, EQB_BILINEAR, T, 4, true>(p, stream);
+  if (fast) {
+    if (sizeof(T) <= 2 && p.use_tma && p.C == 3 && !p.clip && !(p.flags & EQB_FLAG_NO_LEAN))
+      return launch_lean<XF, typename LeanType<T>::type>(p, stream);
+    return launch_staged_one<XF, EQB_BILINEAR, T, 4, true>(p, stream);
+  }
 #endif
   return launch_staged_one<XF, EQB_BILINEAR, T, PX, false>(p, stream);
 }

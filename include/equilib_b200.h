@@ -70,6 +70,8 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 #define EQB_FLAG_FAST_COORDS 32u  /* fp32 images: opt in to the interpolated coordinates  */
 #define EQB_FLAG_FORCE_STAGE 128u /* experiments: staged kernel wherever it is legal           */
 #define EQB_FLAG_NO_TMA 64u       /* staged kernel: cp.async row chunks instead of TMA     */
+#define EQB_FLAG_NO_LEAN 1024u    /* experiments: generic staged kernel where the lean     \
+                                     3-channel variant would run                           */
 /* bits 8..9: force the warp tile shape (0 = auto, 1 = 32x1, 2 = 16x2, 3 = 8x4 lanes) */
 #define EQB_FLAG_WARP_SHAPE_SHIFT 8
 #define EQB_FLAG_WARP_SHAPE(n) ((uint32_t)(n) << EQB_FLAG_WARP_SHAPE_SHIFT)
