@@ -213,7 +213,7 @@ static EncodeTiledFn encode_tiled() {
 // Tensor maps over the source viewed as (W, H, C, B): a wide box for near-upright views,
 // a square one for views rotated by 45 degrees and one in between, all within the
 // kernel's shared-memory budget.
-static void setup_tma(const eqb_remap_desc* d, Params& p) {
+static void setup_tma(const eqb_remap_desc* d, Params& p, bool lean) {
   p.use_tma = 0;
   if (d->flags & EQB_FLAG_NO_TMA) return;
   EncodeTiledFn enc = encode_tiled();
@@ -223,7 +223,7 @@ static void setup_tma(const eqb_remap_desc* d, Params& p) {
   int bw[kTmaBoxes], bh[kTmaBoxes];
   for (int m = 0; m < kTmaBoxes; ++m) {
     bw[m] = box_w(elt, m);
-    bh[m] = box_h(elt, d->channels, m);
+    bh[m] = lean ? lean_box_h(elt, m) : box_h(elt, d->channels, m);
   }
   if (bh[3] < 20) return;  // (more than 4 channels of 4-byte pixels)
   CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
@@ -267,11 +267,24 @@ static bool can_fast(const eqb_remap_desc* d) {
   return true;
 }
 
+// The lean variant of the fast-coordinate kernel: three channels of 1- or 2-byte pixels,
+// no clamp (remap_lean_kernel; its boxes differ, so the choice is made before the
+// tensor maps are encoded).
+static bool can_lean(const eqb_remap_desc* d) {
+  return can_fast(d) && d->channels == 3 && d->dtype != EQB_F32 && !d->clip &&
+         !(d->flags & (EQB_FLAG_NO_LEAN | EQB_FLAG_NO_TMA));
+}
+
 template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int px,
                                         cudaStream_t s) {
   if (can_stage(d)) {
-    setup_tma(d, p);
-    return launch_staged<XF>(p, d->mode, d->dtype, can_fast(d), s);
+    bool lean = can_lean(d);
+    setup_tma(d, p, lean);
+    if (lean && !p.use_tma) {  // no encoder / unaligned strides: generic boxes
+      lean = false;
+      setup_tma(d, p, false);
+    }
+    return launch_staged<XF>(p, d->mode, d->dtype, can_fast(d), lean, s);
   }
   return launch_remap<XF>(p, d->mode, d->dtype, px, pick_ws(d), s);
 }

@@ -93,13 +93,15 @@ static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
 // through TMA (the headline case).
 template <int XF, typename T>
 static cudaError_t launch_lean(Params p, cudaStream_t stream) {
-  using G = StagedGeom<4>;
-  const int smem = staged_smem_bytes((int)sizeof(T));
-  const long long tiles_x = (p.dw + G::tile_w - 1) / G::tile_w;
-  const long long tiles_y = (p.dh + G::tile_h - 1) / G::tile_h;
-  p.iters = tiles_x * tiles_y * p.B >= 148ll * 64 ? 4 : 1;
+  const long long tiles_x = (p.dw + 63) / 64;
+  const long long tiles_y = (p.dh + kLeanTileH - 1) / kLeanTileH;
+  // tiles a CTA walks along x: as many as keep >= 16 waves of CTAs in the grid (the
+  // per-CTA setup -- tables, matrix, row terms -- is ~140 instructions per thread)
+  const long long tiles = tiles_x * tiles_y * p.B;
+  const long long wave = 148ll * 2048 / (kLeanWarps * 32);
+  p.iters = tiles >= wave * 16 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
-  remap_lean_kernel<XF, T><<<grid, kWarps * 32, smem, stream>>>(p);
+  remap_lean_kernel<XF, T><<<grid, kLeanWarps * 32, lean_smem_bytes(), stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -112,12 +114,13 @@ static cudaError_t launch_staged_one(const Params& p, cudaStream_t stream) {
 // bilinear: PX per dtype, or the 4-pixel fast-coordinate variant; bicubic: exact
 // coordinates, 2 pixels per lane (8 cubic weights per pixel are live in the blend)
 template <int XF, typename T, int PX>
-static cudaError_t launch_staged_t(const Params& p, int mode, bool fast, cudaStream_t stream) {
+static cudaError_t launch_staged_t(const Params& p, int mode, bool fast, bool lean,
+                                   cudaStream_t stream) {
   if (mode == EQB_BICUBIC) return launch_staged_one<XF, EQB_BICUBIC, T, 2, false>(p, stream);
 #if EQB_XF <= 2  // transforms with a transcendental chain have a fast-coordinate variant
          // (enum values are invisible to the preprocessor: 0..2 = equi2equi/pers/cube)
   if (fast) {
-    if (sizeof(T) <= 2 && p.use_tma && p.C == 3 && !p.clip && !(p.flags & EQB_FLAG_NO_LEAN))
+    if (lean)
       return launch_lean<XF, typename LeanType<T>::type>(p, stream);
     return launch_staged_one<XF, EQB_BILINEAR, T, 4, true>(p, stream);
   }
@@ -126,13 +129,13 @@ static cudaError_t launch_staged_t(const Params& p, int mode, bool fast, cudaStr
 }
 
 template <>
-cudaError_t launch_staged<EQB_XF>(const Params& p, int mode, int dtype, bool fast,
+cudaError_t launch_staged<EQB_XF>(const Params& p, int mode, int dtype, bool fast, bool lean,
                                   cudaStream_t stream) {
   switch (dtype) {
-    case EQB_U8: return launch_staged_t<EQB_XF, uint8_t, 4>(p, mode, fast, stream);
-    case EQB_F16: return launch_staged_t<EQB_XF, __half, 2>(p, mode, fast, stream);
-    case EQB_BF16: return launch_staged_t<EQB_XF, __nv_bfloat16, 2>(p, mode, fast, stream);
-    case EQB_F32: return launch_staged_t<EQB_XF, float, 2>(p, mode, fast, stream);
+    case EQB_U8: return launch_staged_t<EQB_XF, uint8_t, 4>(p, mode, fast, lean, stream);
+    case EQB_F16: return launch_staged_t<EQB_XF, __half, 2>(p, mode, fast, lean, stream);
+    case EQB_BF16: return launch_staged_t<EQB_XF, __nv_bfloat16, 2>(p, mode, fast, lean, stream);
+    case EQB_F32: return launch_staged_t<EQB_XF, float, 2>(p, mode, fast, lean, stream);
   }
   return cudaErrorInvalidValue;
 }
