@@ -85,7 +85,7 @@ static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
   const long long tiles_y = (p.dh + G::tile_h - 1) / G::tile_h;
   p.iters = tiles_x * tiles_y * p.B >= 148ll * 64 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
-  remap_staged_kernel<XF, MODE, T, PX, FAST, CLIP><<<grid, kWarps * 32, smem, stream>>>(p);
+  remap_staged_kernel<XF, MODE, T, PX, FAST, CLIP><<<grid, kStWarps * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
