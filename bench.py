@@ -352,10 +352,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": ("eqb::remap_kernel<EQUI2EQUI,BILINEAR,float> (direct gather)"
+                     "kernel": ("eqb::remap_staged_kernel<EQUI2EQUI,BILINEAR,float,PX=2> "
+                                "(TMA-staged, exact coordinates)"
                                 if wl["dtype"] == "float32" else
-                                "eqb::remap_staged_kernel<EQUI2EQUI,%s,PX=4,FAST> (TMA-staged)"
-                                % wl["dtype"])},
+                                "eqb::remap_lean_kernel<EQUI2EQUI,%s> (TMA-staged, fast "
+                                "coordinates, 4-warp CTAs)" % wl["dtype"])},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
     }
