@@ -79,7 +79,7 @@ def require_cuda_tensor(x, name: str) -> None:
         )
 
 
-def check_image(img: torch.Tensor, name: str) -> torch.Tensor:
+def check_image(img: torch.Tensor, name: str, allow_channels_last: bool = False) -> torch.Tensor:
     assert len(img.shape) == 4, (
         f"ERR: input `{name}` should be 4-dim (b, c, h, w), but got {len(img.shape)}"
     )
@@ -89,9 +89,18 @@ def check_image(img: torch.Tensor, name: str) -> torch.Tensor:
     )
     if img.dtype == torch.float64:
         raise NotImplementedError("float64 images are not implemented by equilib_b200")
-    if img.stride(3) != 1:
+    if img.stride(3) != 1 and not (allow_channels_last and is_channels_last_u8(img)):
         img = img.contiguous()
     return img
+
+
+def is_channels_last_u8(img: torch.Tensor) -> bool:
+    """uint8 RGB / RGBX in torch.channels_last memory format -- what video decoders hand
+    over.  equi2equi / equi2pers bilinear read and write this layout in
+    place; every other call converts to planar first (``remap_new``)."""
+    return (img.dim() == 4 and img.dtype == torch.uint8 and img.shape[1] in (3, 4)
+            and img.stride(1) == 1 and img.stride(3) == img.shape[1]
+            and img.stride(2) >= img.shape[1] * img.shape[3])
 
 
 def normalise_single(img: torch.Tensor, rots: Rot):
@@ -167,18 +176,43 @@ def mode_code(mode: str) -> int:
     return _lib.MODES[mode]
 
 
+def remap_new(src: torch.Tensor, out_shape, *, allow_channels_last: bool = False,
+              **kw) -> torch.Tensor:
+    """Allocate the output and launch.  A channels-last uint8 source keeps its layout
+    (output in torch.channels_last too) where the library serves it; otherwise it is
+    converted to planar, like every input of the reference."""
+    if src.stride(3) != 1:
+        if allow_channels_last:
+            out = torch.empty(out_shape, dtype=src.dtype, device=src.device,
+                              memory_format=torch.channels_last)
+            cl = dict(kw, flags=kw["flags"] | _lib.FLAG_CHANNELS_LAST,
+                      src_strides=src.stride()[:3], dst_strides=out.stride()[:3])
+            if launch(src, out, probe_channels_last=True, **cl):
+                return out
+        src = src.contiguous()
+    out = torch.empty(out_shape, dtype=src.dtype, device=src.device)
+    launch(src, out, src_strides=src.stride()[:3], dst_strides=out.stride()[:3], **kw)
+    return out
+
+
 def launch(src: torch.Tensor, out: torch.Tensor, *, transform: int, mode: str, flags: int,
            batch: int, channels: int, src_hw: Tuple[int, int], dst_hw: Tuple[int, int],
            src_strides: Sequence[int], dst_strides: Sequence[int], mats=None, tab_x=None,
            tab_y=None, itab_x=None, grid=None, grid_stride_b: int = 0, clip=None,
            w_face: int = 0, n_cells: int = 0, cell_offset: Optional[Sequence[int]] = None,
-           face_ptrs=None) -> None:
+           face_ptrs=None, probe_channels_last: bool = False) -> bool:
+    """One eqb_remap launch.  ``probe_channels_last``: ask the library first whether it
+    serves this channels-last call; returns False without launching if it does not."""
     offs = list(cell_offset) if cell_offset is not None else []
     offs = offs + [0] * (12 - len(offs))
-    _ops.remap(
+    args = (
         src, out, mats, tab_x, tab_y, itab_x, grid, clip, face_ptrs,
         transform, mode_code(mode), flags, batch, channels,
         src_hw[0], src_hw[1], dst_hw[0], dst_hw[1],
         [int(s) for s in src_strides], [int(s) for s in dst_strides],
         int(grid_stride_b), w_face, n_cells, offs,
     )
+    if probe_channels_last and not _ops.supports_channels_last(*args):
+        return False
+    _ops.remap(*args)
+    return True

@@ -28,6 +28,7 @@ FLAG_FAST_COORDS = 32
 FLAG_NO_TMA = 64
 FLAG_FORCE_STAGE = 128
 FLAG_NO_LEAN = 1024
+FLAG_CHANNELS_LAST = 2048
 FLAG_WARP_SHAPE_SHIFT = 8
 
 MODES = {"nearest": NEAREST, "bilinear": BILINEAR, "bicubic": BICUBIC}
@@ -85,6 +86,7 @@ EXPORTS = {
     "eqb_abi_version": (C.c_int32, []),
     "eqb_last_error": (C.c_char_p, []),
     "eqb_remap": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p]),
+    "eqb_remap_supports_channels_last": (C.c_int32, [C.POINTER(RemapDesc)]),
     "eqb_remap_coords": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p, C.c_void_p]),
     "eqb_minmax": (C.c_int32, [C.POINTER(Image), C.c_void_p, C.c_void_p]),
     "eqb_rotation_compose": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),

@@ -117,6 +117,17 @@ def _remap_impl(
         _lib.check(_lib.lib().eqb_remap(C.byref(d), C.c_void_p(stream)), "eqb_remap")
 
 
+def supports_channels_last(src, out, mats, tab_x, tab_y, itab_x, grid, clip, face_ptrs,
+                           transform, mode, flags, batch, channels, src_h, src_w, dst_h, dst_w,
+                           src_strides, dst_strides, grid_stride_b, w_face, n_cells,
+                           cell_offset) -> bool:
+    """eqb_remap_supports_channels_last for the arguments of ``remap`` (host only)."""
+    d = _fill_desc(src, out, mats, tab_x, tab_y, itab_x, grid, clip, transform, mode, flags,
+                   batch, channels, src_h, src_w, dst_h, dst_w, src_strides, dst_strides,
+                   grid_stride_b, w_face, n_cells, cell_offset, face_ptrs)
+    return bool(_lib.lib().eqb_remap_supports_channels_last(C.byref(d)))
+
+
 # The registered op (torch.ops.equilib_b200.remap) is what graph capture / torch.compile
 # see; eager callers go straight to the implementation and skip ~50 us of dispatcher
 # overhead per call, which dominates small launches (BASELINE config 1 is a 5 us kernel).

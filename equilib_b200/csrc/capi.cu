@@ -275,8 +275,66 @@ static bool can_lean(const eqb_remap_desc* d) {
          !(d->flags & (EQB_FLAG_NO_LEAN | EQB_FLAG_NO_TMA));
 }
 
+// Channels-last uint8 (EQB_FLAG_CHANNELS_LAST): served by the channels-last variant of the
+// lean kernel only -- RGB / RGBX, bilinear, fast coordinates, equi2equi / equi2pers, TMA.
+static bool can_nhwc(const eqb_remap_desc* d) {
+  if (d->dtype != EQB_U8 || (d->channels != 3 && d->channels != 4)) return false;
+  if (d->mode != EQB_BILINEAR || d->transform > EQB_EQUI2PERS) return false;
+  if (d->flags & (EQB_FLAG_EXACT_COORDS | EQB_FLAG_NO_STAGE | EQB_FLAG_NO_TMA)) return false;
+  if (d->clip || !encode_tiled()) return false;
+  const long long c = d->channels;
+  if (d->src_stride_c != 1 || d->dst_stride_c != 1) return false;
+  if (d->src_stride_h < c * d->src_w || d->dst_stride_h < c * d->dst_w) return false;
+  // source rows as 32-bit words under 16-byte aligned strides (TMA)
+  if (reinterpret_cast<uintptr_t>(d->src) % 16 || d->src_stride_h % 16 || d->src_stride_b % 16)
+    return false;
+  if ((c * d->src_w) % 4) return false;
+  // 4-pixel vector stores: 16 (RGBX) or 12 (RGB) bytes per lane
+  const long long va = c == 4 ? 16 : 4;
+  if (reinterpret_cast<uintptr_t>(d->dst) % va || d->dst_stride_h % va || d->dst_stride_b % va)
+    return false;
+  if (d->src_w > 65536 || d->src_h > 65536 || d->src_w < 4 || d->src_h < 4) return false;
+  if ((long long)d->src_stride_h * d->src_h >= (1ll << 31)) return false;
+  return (long long)d->batch * d->dst_h * d->dst_w >= (1ll << 18);
+}
+
+// Tensor maps for the channels-last kernel: a source row is W*C/4 32-bit words.
+static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
+  p.use_tma = 0;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return;
+  const int c = d->channels;
+  const bool batched = d->src_stride_b > 0 && d->batch > 1;
+  const cuuint64_t row = (cuuint64_t)d->src_stride_h;  // bytes (uint8)
+  const cuuint64_t dims[4] = {(cuuint64_t)d->src_w * c / 4, (cuuint64_t)d->src_h, 1,
+                              (cuuint64_t)(batched ? d->batch : 1)};
+  const cuuint64_t strides[3] = {row, row * d->src_h,
+                                 batched ? (cuuint64_t)d->src_stride_b : row * d->src_h};
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
+  for (int m = 0; m < kTmaBoxes; ++m) {
+    const int bw = box_w(1, m), bh = lean_box_h(1, m, c);
+    if (bw * c / 4 > 256) continue;  // (box dimensions are limited to 256 elements)
+    const cuuint32_t box[4] = {(cuuint32_t)(bw * c / 4), (cuuint32_t)bh, 1, 1};
+    if (enc(&p.tmaps[m], CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(d->src), dims,
+            strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return;
+    p.tma_bw[m] = bw;
+    p.tma_bh[m] = bh;
+  }
+  p.tma_batched = batched ? 1 : 0;
+  p.use_tma = 1;
+}
+
 template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int px,
                                         cudaStream_t s) {
+  if (d->flags & EQB_FLAG_CHANNELS_LAST) {
+    // (eqb_remap has checked can_nhwc)
+    setup_tma_nhwc(d, p);
+    if (!p.use_tma) return cudaErrorNotSupported;
+    return launch_nhwc<XF>(p, s);
+  }
   if (can_stage(d)) {
     bool lean = can_lean(d);
     setup_tma(d, p, lean);
@@ -371,6 +429,10 @@ int32_t eqb_remap(const eqb_remap_desc* d, void* stream) {
   Params p;
   const int rc = fill(d, true, p);
   if (rc != EQB_OK) return rc;
+  if ((d->flags & EQB_FLAG_CHANNELS_LAST) && !can_nhwc(d))
+    return fail(EQB_ERR_UNSUPPORTED,
+                "channels-last layout is served for uint8 RGB/RGBX bilinear equi2equi/equi2pers "
+                "on large aligned launches only (eqb_remap_supports_channels_last)");
   const int px = pick_px(d);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;
@@ -387,6 +449,15 @@ int32_t eqb_remap(const eqb_remap_desc* d, void* stream) {
   g_launches.fetch_add(1);
   g_err[0] = 0;
   return EQB_OK;
+}
+
+int32_t eqb_remap_supports_channels_last(const eqb_remap_desc* d) {
+  Params p;
+  if (fill(d, true, p) != EQB_OK) {
+    g_err[0] = 0;
+    return 0;
+  }
+  return can_nhwc(d) ? 1 : 0;
 }
 
 int32_t eqb_remap_coords(const eqb_remap_desc* d, float* coords_out, void* stream) {

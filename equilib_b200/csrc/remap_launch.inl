@@ -140,6 +140,30 @@ cudaError_t launch_staged<EQB_XF>(const Params& p, int mode, int dtype, bool fas
   return cudaErrorInvalidValue;
 }
 
+// Channels-last uint8 RGB / RGBX (EQB_FLAG_CHANNELS_LAST): the lean kernel's IL variants.
+template <int XF, int IL>
+static cudaError_t launch_nhwc_il(Params p, cudaStream_t stream) {
+  const long long tiles_x = (p.dw + 63) / 64;
+  const long long tiles_y = (p.dh + kLeanTileH - 1) / kLeanTileH;
+  const long long tiles = tiles_x * tiles_y * p.B;
+  const long long wave = 148ll * 2048 / (kLeanWarps * 32);
+  p.iters = tiles >= wave * 16 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
+  const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
+  // (+16: the RGB tap loads are aligned words that may end past the last tap)
+  remap_lean_kernel<XF, uint8_t, IL>
+      <<<grid, kLeanWarps * 32, lean_smem_bytes() + 16, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_nhwc<EQB_XF>(const Params& p, cudaStream_t stream) {
+#if EQB_XF <= 1  // equi2equi, equi2pers
+  if (p.C == 4) return launch_nhwc_il<EQB_XF, 4>(p, stream);
+  if (p.C == 3) return launch_nhwc_il<EQB_XF, 3>(p, stream);
+#endif
+  return cudaErrorNotSupported;
+}
+
 template <>
 cudaError_t launch_coords<EQB_XF>(const Params& p, bool libm, cudaStream_t stream) {
   const dim3 grid((p.dw + 31) / 32, (p.dh + 7) / 8, p.B);

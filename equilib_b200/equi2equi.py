@@ -73,7 +73,7 @@ def run(src, rots, z_down, mode, height=None, width=None, clip_output=True,
         opt: K.Options = None) -> torch.Tensor:
     """Replaces equilib/equi2equi/torch.py:45-200 with one fused launch."""
     opt = opt or K.Options()
-    src = K.check_image(src, "src")
+    src = K.check_image(src, "src", allow_channels_last=True)
     assert len(src) == len(rots), (
         f"ERR: length of `src` and `rot` differs: {len(src)} vs {len(rots)}"
     )
@@ -91,11 +91,9 @@ def run(src, rots, z_down, mode, height=None, width=None, clip_output=True,
     mats = _prep.mats_for("rot", rots, z_down, dev)
     tab_x, tab_y = _prep.equirect_tables(height, width, dev)
     clip = K.clip_tensor(src, mode, clip_output, opt.exact_clip, group=opt.clip_group)
-    out = torch.empty((bs, c, height, width), dtype=src.dtype, device=dev)
-    K.launch(
-        src, out, transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, opt),
+    return K.remap_new(
+        src, (bs, c, height, width), allow_channels_last=mode == "bilinear",
+        transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, opt),
         batch=bs, channels=c, src_hw=(h_equi, w_equi), dst_hw=(height, width),
-        src_strides=src.stride()[:3], dst_strides=out.stride()[:3],
         mats=mats, tab_x=tab_x, tab_y=tab_y, clip=clip,
     )
-    return out

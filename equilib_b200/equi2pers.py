@@ -96,7 +96,7 @@ def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
         opt: K.Options = None) -> torch.Tensor:
     """Replaces equilib/equi2pers/torch.py:96-244 with one fused launch."""
     opt = opt or K.Options()
-    equi = K.check_image(equi, "equi")
+    equi = K.check_image(equi, "equi", allow_channels_last=True)
     assert len(equi) == len(rots), (
         f"ERR: length of equi and rot differs: {len(equi)} vs {len(rots)}"
     )
@@ -106,14 +106,12 @@ def run(equi, rots, height, width, fov_x, skew, z_down, mode, clip_output=True,
     mats = _prep.mats_for("equi2pers", rots, z_down, dev,
                           (int(height), int(width), float(fov_x), float(skew)))
     clip = K.clip_tensor(equi, mode, clip_output, opt.exact_clip, group=opt.clip_group)
-    out = torch.empty((bs, c, height, width), dtype=equi.dtype, device=dev)
-    K.launch(
-        equi, out, transform=_lib.EQUI2PERS, mode=mode,
+    return K.remap_new(
+        equi, (bs, c, height, width), allow_channels_last=mode == "bilinear",
+        transform=_lib.EQUI2PERS, mode=mode,
         flags=K.flags_of(equi.dtype, opt), batch=bs, channels=c,
-        src_hw=(h_equi, w_equi), dst_hw=(height, width),
-        src_strides=equi.stride()[:3], dst_strides=out.stride()[:3], mats=mats, clip=clip,
+        src_hw=(h_equi, w_equi), dst_hw=(height, width), mats=mats, clip=clip,
     )
-    return out
 
 
 def get_bounding_fov(
@@ -133,7 +131,7 @@ def get_bounding_fov(
     (``eqb_remap_coords``); only the perimeter is copied back to the host."""
     K.require_cuda_tensor(equi, "equi")
     equi, rots, is_single = K.normalise_single(equi, rots)
-    equi = K.check_image(equi, "equi")
+    equi = K.check_image(equi, "equi", allow_channels_last=True)
     assert len(equi) == len(rots), (
         f"ERR: length of equi and rot differs: {len(equi)} vs {len(rots)}"
     )

@@ -72,6 +72,13 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 #define EQB_FLAG_NO_TMA 64u       /* staged kernel: cp.async row chunks instead of TMA     */
 #define EQB_FLAG_NO_LEAN 1024u    /* experiments: generic staged kernel where the lean     \
                                      3-channel variant would run                           */
+#define EQB_FLAG_CHANNELS_LAST 2048u /* src and dst are channels-last (NHWC): channel stride  \
+                                       1, pixel stride = channels; strides_h in elements.     \
+                                       Served for uint8 RGB / RGBX bilinear equi2equi and     \
+                                       equi2pers on large launches (the layout   \
+                                       video decoders hand over; the reference converts HWC    \
+                                       to CHW on the host, scripts/equi2pers_torch.py:29-44); \
+                                       see eqb_remap_supports_channels_last                   */
 /* bits 8..9: force the warp tile shape (0 = auto, 1 = 32x1, 2 = 16x2, 3 = 8x4 lanes) */
 #define EQB_FLAG_WARP_SHAPE_SHIFT 8
 #define EQB_FLAG_WARP_SHAPE(n) ((uint32_t)(n) << EQB_FLAG_WARP_SHAPE_SHIFT)
@@ -151,6 +158,13 @@ const char* eqb_last_error(void);
 
 /* Fused ray generation + ray-to-pixel map + sampling + output policy. */
 int32_t eqb_remap(const eqb_remap_desc* desc, void* stream);
+
+/*
+ * 1 when eqb_remap serves `desc` with EQB_FLAG_CHANNELS_LAST set (the flag itself need not
+ * be set in `desc`), else 0: the caller then converts to the planar layout, as
+ * equilib/equi2pers/base.py does for every input.  Host only, no launch.
+ */
+int32_t eqb_remap_supports_channels_last(const eqb_remap_desc* desc);
 
 /*
  * Writes the sampling coordinates of the transform (what the reference calls

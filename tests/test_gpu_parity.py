@@ -715,3 +715,71 @@ def test_equi2cube_fast_coordinates_faces_of_64():
         ref = oracle.equi2cube(img, rots, w_face, "dice", flavour="cuda")
         d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
         assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.97
+
+
+# --- channels-last uint8 -------------------------------------------------
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+@pytest.mark.parametrize("transform", ["equi2equi", "equi2pers"])
+def test_channels_last_uint8_in_place(transform, channels):
+    """A uint8 RGB / RGBX batch in torch.channels_last (what decoders hand over) is read
+    and written in that layout: same values as the planar call, within one code value of
+    the oracle, output in channels_last too."""
+    shape = (2, channels, 512, 1024)
+    img = torch.from_numpy(0.5 * cases.band_limited_image(shape, "float32", px=96, py=64) * 255
+                           + 0.5 * cases.noise_image(shape, "uint8", 5)).to(torch.uint8)
+    rots = HARD_ROTS[1:3]
+    args = () if transform == "equi2equi" else (512, 768, 100.0)
+    fn = getattr(equilib_b200, transform)
+    planar = fn(img.to(DEV), rots, *args)
+    x_cl = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    n0 = _lib.lib().eqb_launch_count()
+    out = fn(x_cl, rots, *args)
+    assert _lib.lib().eqb_launch_count() == n0 + 1
+    assert out.shape == planar.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert not out.is_contiguous()
+    d = (out.int() - planar.int()).abs()
+    assert int(d.max()) <= 1 and float((d == 0).float().mean()) >= 0.999
+    ref = getattr(oracle, transform)(img, rots, *args, flavour="cuda")
+    d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
+    assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.97
+
+
+def test_channels_last_ragged_and_pole_tiles():
+    """Widths that are not multiples of the 64-pixel tile, a view looking at a pole (tiles
+    that fit no box gather from global memory) and the right image edge."""
+    img = torch.from_numpy(cases.noise_image((2, 3, 512, 1040), "uint8", 11))
+    rots = [HARD_ROTS[0], {"roll": 0.3, "pitch": math.pi / 2 - 0.05, "yaw": 1.0}]
+    x_cl = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    out = equilib_b200.equi2equi(x_cl, rots, height=516, width=1036)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    ref = oracle.equi2equi(img, rots, height=516, width=1036, flavour="cuda")
+    d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
+    assert np.mean(d <= 1) >= 0.9995 and np.mean(d == 0) >= 0.97
+
+
+def test_channels_last_falls_back_to_planar_where_not_served():
+    img = torch.from_numpy(cases.noise_image((1, 3, 128, 256), "uint8", 3))
+    x_cl = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    rots = [HARD_ROTS[1]]
+    # small launch, bicubic, another transform: converted like every input of the reference
+    for out, want in (
+        (equilib_b200.equi2equi(x_cl, rots), equilib_b200.equi2equi(img.to(DEV), rots)),
+        (equilib_b200.equi2equi(x_cl, rots, mode="bicubic"),
+         equilib_b200.equi2equi(img.to(DEV), rots, mode="bicubic")),
+        (equilib_b200.equi2cube(x_cl, rots, 64, "horizon"),
+         equilib_b200.equi2cube(img.to(DEV), rots, 64, "horizon")),
+    ):
+        assert out.is_contiguous() and torch.equal(out, want)
+    # the C ABI refuses the flag where the kernel does not exist
+    big = torch.zeros((1, 3, 512, 1024), dtype=torch.float16, device=DEV)
+    big = big.contiguous(memory_format=torch.channels_last)
+    with pytest.raises(_lib.EquilibB200Error, match="channels-last"):
+        from equilib_b200 import _common as K
+        tab_x, tab_y = _prep.equirect_tables(512, 1024, DEV)
+        K.launch(big, torch.empty_like(big), transform=_lib.EQUI2EQUI, mode="bilinear",
+                 flags=_lib.FLAG_CHANNELS_LAST, batch=1, channels=3, src_hw=(512, 1024),
+                 dst_hw=(512, 1024), src_strides=big.stride()[:3],
+                 dst_strides=big.stride()[:3],
+                 mats=_prep.mats_for("rot", rots, False, DEV), tab_x=tab_x, tab_y=tab_y)

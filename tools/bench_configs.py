@@ -86,6 +86,20 @@ def main():
                    b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 4)
         del src
 
+    # uint8 RGB / RGBX in channels-last layout (what decoders hand over), read
+    # and written in place, next to the planar layout of the same frames
+    for c in (3, 4):
+        src = frames(32, c, 2048, 4096, torch.uint8)
+        r = rots(32)
+        px = 32 * 2048 * 4096
+        ms = timed(lambda: equilib_b200.equi2equi(src, r))
+        report(f"N1: equi2equi uint8 b32 4K bilinear, {c} channels, planar", ms, px, 2 * px * c)
+        src_cl = src.contiguous(memory_format=torch.channels_last)
+        ms = timed(lambda: equilib_b200.equi2equi(src_cl, r))
+        report(f"N1: equi2equi uint8 b32 4K bilinear, {c} channels, channels-last", ms, px,
+               2 * px * c)
+        del src, src_cl
+
     # config 3: equi2cube + cube2equi, batch 16, w_face 1024, fp32 and uint8
     for dtype in (torch.float32, torch.uint8):
         equi = frames(16, 3, 2048, 4096, dtype)
