@@ -96,6 +96,21 @@ def main():
         d = torch.minimum(d, 256 - d)
         print(json.dumps({"case": f"equi2equi/u8/{mode}", "max": int(d.max()),
                           "frac_equal": float((d == 0).float().mean())}), flush=True)
+    # channels-last uint8 against the reference fed the planar frames
+    for ch in (3, 4):
+        x = torch.from_numpy(cases.noise_image((2, ch, h, w), "uint8", 2)).to(dev)
+        ref = equilib.equi2equi(x.clone(), rots, mode="bilinear")
+        out = equilib_b200.equi2equi(x.contiguous(memory_format=torch.channels_last), rots)
+        d = (out.int() - ref.int()).abs()
+        print(json.dumps({"case": f"equi2equi/u8 channels-last C={ch}/bilinear", "max": int(d.max()),
+                          "frac_equal": float((d == 0).float().mean()),
+                          "channels_last_out": bool(out.is_contiguous(
+                              memory_format=torch.channels_last))}), flush=True)
+    # bf16 (rejected by the reference): against the reference's fp32 result rounded once
+    bf = imgs["band"].bfloat16()
+    ref32 = equilib.equi2equi(bf.float(), rots, mode="bilinear")
+    out = equilib_b200.equi2equi(bf, rots, mode="bilinear")
+    stats("equi2equi/bf16 vs reference-fp32 rounded to bf16", out, ref32.bfloat16())
     f16 = imgs["band"].half()
     ref16 = equilib.equi2equi(f16.clone(), rots, mode="bilinear")
     ref32 = equilib.equi2equi(imgs["band"].clone(), rots, mode="bilinear")
