@@ -95,11 +95,11 @@ template <int XF, typename T>
 static cudaError_t launch_lean(Params p, cudaStream_t stream) {
   const long long tiles_x = (p.dw + 63) / 64;
   const long long tiles_y = (p.dh + kLeanTileH - 1) / kLeanTileH;
-  // tiles a CTA walks along x: as many as keep >= 16 waves of CTAs in the grid (the
-  // per-CTA setup -- tables, matrix, row terms -- is ~140 instructions per thread)
+  // tiles a CTA walks along x: 16 where that leaves >= 8 waves of CTAs in the grid (the
+  // per-CTA setup -- tables, matrix, row terms -- is ~180 instructions per thread)
   const long long tiles = tiles_x * tiles_y * p.B;
   const long long wave = 148ll * 2048 / (kLeanWarps * 32);
-  p.iters = tiles >= wave * 16 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
+  p.iters = tiles >= wave * 8 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
   remap_lean_kernel<XF, T><<<grid, kLeanWarps * 32, lean_smem_bytes(), stream>>>(p);
   return cudaGetLastError();
@@ -147,7 +147,7 @@ static cudaError_t launch_nhwc_il(Params p, cudaStream_t stream) {
   const long long tiles_y = (p.dh + kLeanTileH - 1) / kLeanTileH;
   const long long tiles = tiles_x * tiles_y * p.B;
   const long long wave = 148ll * 2048 / (kLeanWarps * 32);
-  p.iters = tiles >= wave * 16 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
+  p.iters = tiles >= wave * 8 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
   // (+16: the RGB tap loads are aligned words that may end past the last tap)
   remap_lean_kernel<XF, uint8_t, IL>
