@@ -18,6 +18,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import equilib_b200  # noqa: E402
+from equilib_b200 import _lib, _ops, _prep  # noqa: E402
 
 DEV = torch.device("cuda", 0)
 
@@ -85,6 +86,30 @@ def main():
             report("2: equi2equi float32 b16 4K bilinear fast_coords=True (opt-in)", ms,
                    b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 4)
         del src
+
+    # config 2 comparator: torch.nn.functional.grid_sample on the same GPU, fed a
+    # pre-built on-device normalised grid of the same rotations (grid build time excluded:
+    # the reference builds it on the CPU, ~0.1 s per 4K frame).  Benchmark context only; the
+    # product never calls grid_sample.
+    import torch.nn.functional as F
+    for dtype, b in ((torch.bfloat16, 32), (torch.float32, 16)):
+        src = frames(b, 3, 2048, 4096, dtype)
+        r = rots(b)
+        tab_x, tab_y = _prep.equirect_tables(2048, 4096, DEV)
+        coords = torch.empty((b, 2, 2048, 4096), dtype=torch.float32, device=DEV)
+        _ops.coords(coords, _prep.mats_for("rot", r, False, DEV), tab_x, tab_y, None, None,
+                    _lib.EQUI2EQUI, b, 2048, 4096, 2048, 4096)
+        gx = (2 * coords[:, 1] / (4096 - 1) - 1)
+        gy = (2 * coords[:, 0] / (2048 - 1) - 1)
+        grid = torch.stack((gx, gy), dim=-1).to(dtype).contiguous()
+        del coords, gx, gy
+        ms = timed(lambda: F.grid_sample(src, grid, mode="bilinear", padding_mode="reflection",
+                                         align_corners=True), steps=5)
+        px = b * 2048 * 4096
+        report(f"2: comparator torch F.grid_sample {str(dtype)[6:]} b{b} 4K bilinear, grid pre-built "
+               "on device", ms, px, 2 * px * 3 * src.element_size(),
+               note="reads an extra %d B/px of grid" % (2 * src.element_size()))
+        del src, grid
 
     # uint8 RGB / RGBX in channels-last layout (what decoders hand over), read
     # and written in place, next to the planar layout of the same frames
