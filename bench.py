@@ -63,9 +63,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def bench_rotations(n, offset=0):
+def bench_rotations(n, offset=0, rank=0):
+    """n distinct rotations (roll 0.01 i, pitch 0.4 sin i, yaw 0.05 i: the pattern of the
+    reference's benchmarks/cache_benchmark.py:37-40).  Every rank of a multi-GPU run gets
+    the same roll / pitch pattern under its own yaw shift: rotations stay distinct across
+    the job while the per-GPU work is the same on every rank (weak scaling), instead of
+    later ranks getting ever more strongly rolled -- and more expensive -- views."""
     return [{"roll": 0.01 * (i + offset), "pitch": 0.4 * math.sin(i + offset),
-             "yaw": 0.05 * (i + offset)} for i in range(n)]
+             "yaw": 0.05 * (i + offset) + 0.61 * rank} for i in range(n)]
 
 
 def synth_frames(wl, device, seed):
@@ -264,7 +269,7 @@ def main():
 
     b, c, h, w = wl["batch"], wl["c"], wl["h"], wl["w"]
     src = synth_frames(wl, dev, seed=rank)
-    rots = bench_rotations(b, offset=rank * b)
+    rots = bench_rotations(b, rank=rank)
     op = equilib_b200.Equi2Equi(mode=wl["mode"])
 
     for _ in range(args.warmup):

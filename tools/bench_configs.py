@@ -81,6 +81,13 @@ def main():
             px = b * 2048 * 4096
             report(f"2: equi2equi {str(dtype)[6:]} b{b} 4K {mode}", ms, px,
                    2 * px * 3 * src.element_size())
+        if dtype == torch.bfloat16:
+            # the same views rolled by a further 55-73 degrees: the 64-pixel side of a tile
+            # then runs down the source columns (tall boxes)
+            rr = [dict(x, roll=x["roll"] + 0.96) for x in r]
+            ms = timed(lambda: equilib_b200.equi2equi(src, rr))
+            report("2: equi2equi bfloat16 b32 4K bilinear, views rolled by a further 0.96 rad", ms,
+                   b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 2)
         if dtype == torch.float32:
             ms = timed(lambda: equilib_b200.equi2equi(src, r, fast_coords=True))
             report("2: equi2equi float32 b16 4K bilinear fast_coords=True (opt-in)", ms,
