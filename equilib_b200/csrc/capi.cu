@@ -32,7 +32,7 @@ static size_t elt_size(int dtype) {
 }
 
 static int vec_px(int dtype, int mode, int transform) {
-  if (mode == EQB_BICUBIC) return 1;
+  if (mode == EQB_BICUBIC && transform != EQB_PERS2EQUI) return 1;  // see launch_px
   if (transform == EQB_CUBE2EQUI && mode == EQB_BILINEAR) return 2;  // see launch_px
   return dtype == EQB_U8 ? 4 : 2;
 }
@@ -132,6 +132,8 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
 // cell) must be aligned to PX elements.
 static int pick_px(const eqb_remap_desc* d) {
   const int v = vec_px(d->dtype, d->mode, d->transform);
+  // (the vectorised bicubic pers2equi holds one result per channel and pixel in registers)
+  if (d->mode == EQB_BICUBIC && d->transform == EQB_PERS2EQUI && d->channels > 4) return 1;
   const size_t bytes = v * elt_size(d->dtype);
   if (reinterpret_cast<uintptr_t>(d->dst) % bytes) return 1;
   if (d->dst_stride_b % v || d->dst_stride_c % v || d->dst_stride_h % v) return 1;

@@ -40,8 +40,11 @@ template <int XF, int MODE, typename T>
 static cudaError_t launch_px(const Params& p, int px, int ws, cudaStream_t stream) {
   if (px == 1) return launch_ws<XF, MODE, T, 1>(p, ws, stream);
   // cube2equi carries one offset and face id per tap: 4 uint8 pixels per thread spill
-  constexpr int V = (XF == EQB_CUBE2EQUI && MODE == EQB_BILINEAR && sizeof(T) == 1)
-                        ? 2 : VecPX<T, MODE>::value;
+  // pers2equi keeps vector stores in bicubic mode (its output is mostly fill)
+  constexpr int V = (XF == EQB_CUBE2EQUI && MODE == EQB_BILINEAR && sizeof(T) == 1) ? 2
+                    : (XF == EQB_PERS2EQUI && MODE == EQB_BICUBIC)
+                        ? VecPX<T, EQB_BILINEAR>::value
+                        : VecPX<T, MODE>::value;
   return launch_ws<XF, MODE, T, V>(p, ws, stream);
 }
 
