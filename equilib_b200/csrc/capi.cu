@@ -225,7 +225,7 @@ static void setup_tma(const eqb_remap_desc* d, Params& p, bool lean) {
   int bw[kTmaBoxes], bh[kTmaBoxes];
   for (int m = 0; m < kTmaBoxes; ++m) {
     bw[m] = box_w(elt, m);
-    bh[m] = lean ? lean_box_h(elt, m) : box_h(elt, d->channels, m);
+    bh[m] = lean ? lean_box_h(elt, m, d->channels) : box_h(elt, d->channels, m);
   }
   if (bh[3] < 20) return;  // (more than 4 channels of 4-byte pixels)
   CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
@@ -269,11 +269,12 @@ static bool can_fast(const eqb_remap_desc* d) {
   return true;
 }
 
-// The lean variant of the fast-coordinate kernel: three channels of 1- or 2-byte pixels,
+// The lean variant of the fast-coordinate kernel: 1, 3 or 4 channels of 1- or 2-byte pixels,
 // no clamp (remap_lean_kernel; its boxes differ, so the choice is made before the
 // tensor maps are encoded).
 static bool can_lean(const eqb_remap_desc* d) {
-  return can_fast(d) && d->channels == 3 && d->dtype != EQB_F32 && !d->clip &&
+  return can_fast(d) && (d->channels == 1 || d->channels == 3 || d->channels == 4) &&
+         d->dtype != EQB_F32 && !d->clip &&
          !(d->flags & (EQB_FLAG_NO_LEAN | EQB_FLAG_NO_TMA));
 }
 

@@ -94,8 +94,8 @@ static cudaError_t launch_staged_clip(Params p, cudaStream_t stream) {
 
 // Lean variant of <BILINEAR, PX 4, FAST, no clip> for three channels of 1- or 2-byte pixels
 // through TMA (the headline case).
-template <int XF, typename T>
-static cudaError_t launch_lean(Params p, cudaStream_t stream) {
+template <int XF, typename T, int NC>
+static cudaError_t launch_lean_nc(Params p, cudaStream_t stream) {
   const long long tiles_x = (p.dw + 63) / 64;
   const long long tiles_y = (p.dh + kLeanTileH - 1) / kLeanTileH;
   // tiles a CTA walks along x: 16 where that leaves >= 8 waves of CTAs in the grid (the
@@ -104,8 +104,18 @@ static cudaError_t launch_lean(Params p, cudaStream_t stream) {
   const long long wave = 148ll * 2048 / (kLeanWarps * 32);
   p.iters = tiles >= wave * 8 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
-  remap_lean_kernel<XF, T><<<grid, kLeanWarps * 32, lean_smem_bytes(), stream>>>(p);
+  remap_lean_kernel<XF, T, 0, NC><<<grid, kLeanWarps * 32, lean_smem_bytes(), stream>>>(p);
   return cudaGetLastError();
+}
+
+template <int XF, typename T>
+static cudaError_t launch_lean(const Params& p, cudaStream_t stream) {
+  switch (p.C) {
+    case 1: return launch_lean_nc<XF, T, 1>(p, stream);
+    case 3: return launch_lean_nc<XF, T, 3>(p, stream);
+    case 4: return launch_lean_nc<XF, T, 4>(p, stream);
+  }
+  return cudaErrorNotSupported;  // (capi.cu::can_lean)
 }
 
 template <int XF, int MODE, typename T, int PX, bool FAST>
