@@ -13,6 +13,7 @@ from .equi2equi import Equi2Equi, equi2equi
 from .equi2pers import Equi2Pers, equi2pers, get_bounding_fov
 from .grid_sample import grid_sample
 from .pers2equi import Pers2Equi, pers2equi
+from .static import StaticRemap
 
 __version__ = "0.1.0"
 
@@ -29,4 +30,5 @@ __all__ = [
     "pers2equi",
     "grid_sample",
     "get_bounding_fov",
+    "StaticRemap",
 ]

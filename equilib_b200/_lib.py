@@ -29,6 +29,7 @@ FLAG_NO_TMA = 64
 FLAG_FORCE_STAGE = 128
 FLAG_NO_LEAN = 1024
 FLAG_CHANNELS_LAST = 2048
+MAP_TILE_W, MAP_TILE_H = 64, 8
 FLAG_WARP_SHAPE_SHIFT = 8
 
 MODES = {"nearest": NEAREST, "bilinear": BILINEAR, "bicubic": BICUBIC}
@@ -88,6 +89,9 @@ EXPORTS = {
     "eqb_remap": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p]),
     "eqb_remap_supports_channels_last": (C.c_int32, [C.POINTER(RemapDesc)]),
     "eqb_remap_coords": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p, C.c_void_p]),
+    "eqb_map_build": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "eqb_remap_mapped": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "eqb_minmax": (C.c_int32, [C.POINTER(Image), C.c_void_p, C.c_void_p]),
     "eqb_rotation_compose": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "eqb_launch_count": (C.c_int64, []),

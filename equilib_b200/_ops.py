@@ -178,3 +178,42 @@ def coords(coords_out: Tensor, mats, tab_x, tab_y, itab_x, grid, transform: int,
                                         C.c_void_p(stream)),
             "eqb_remap_coords",
         )
+
+
+def map_build(coords_t: Tensor, map_t: Tensor, heads_t: Tensor, dtype: torch.dtype, channels: int,
+              mats, tab_x, tab_y, itab_x, transform: int, batch: int, src_h: int, src_w: int,
+              dst_h: int, dst_w: int) -> None:
+    """eqb_map_build: pack the coordinates of a fixed set of rotations into a sampling map."""
+    _require_cuda(coords_t, "coords")
+    d = _fill_desc(None, None, mats, tab_x, tab_y, itab_x, None, None, transform, 1, 0, batch,
+                   channels, src_h, src_w, dst_h, dst_w, (0, 0, 0), (0, 0, 0), 0, 0, 0,
+                   [0] * 12, None)
+    d.dtype = dtype_code(dtype)
+    with torch.cuda.device(coords_t.device):
+        stream = torch.cuda.current_stream(coords_t.device).cuda_stream
+        _lib.check(
+            _lib.lib().eqb_map_build(C.byref(d), C.c_void_p(coords_t.data_ptr()),
+                                     C.c_void_p(map_t.data_ptr()),
+                                     C.c_void_p(heads_t.data_ptr()), C.c_void_p(stream)),
+            "eqb_map_build",
+        )
+
+
+def remap_mapped(src: Tensor, out: Tensor, map_t: Tensor, heads_t: Tensor, mats, tab_x, tab_y,
+                 itab_x, transform: int, flags: int) -> None:
+    """eqb_remap_mapped: ``out`` <- ``src`` sampled through a map from ``map_build``."""
+    _require_cuda(src, "src")
+    _require_cuda(out, "out")
+    if out.device != src.device or out.dtype != src.dtype:
+        raise _lib.EquilibB200Error("src and out must share device and dtype")
+    b, c, sh, sw = src.shape
+    d = _fill_desc(src, out, mats, tab_x, tab_y, itab_x, None, None, transform, 1, flags, b, c,
+                   sh, sw, out.shape[2], out.shape[3], src.stride()[:3], out.stride()[:3], 0, 0,
+                   0, [0] * 12, None)
+    with torch.cuda.device(src.device):
+        stream = torch.cuda.current_stream(src.device).cuda_stream
+        _lib.check(
+            _lib.lib().eqb_remap_mapped(C.byref(d), C.c_void_p(map_t.data_ptr()),
+                                        C.c_void_p(heads_t.data_ptr()), C.c_void_p(stream)),
+            "eqb_remap_mapped",
+        )

@@ -463,6 +463,66 @@ int32_t eqb_remap_supports_channels_last(const eqb_remap_desc* d) {
   return can_nhwc(d) ? 1 : 0;
 }
 
+static_assert(EQB_MAP_TILE_W == 64 && EQB_MAP_TILE_H == kLeanTileH, "map tile == lean tile");
+
+static int map_box_table(const eqb_remap_desc* d, Params& p) {
+  const int elt = (int)elt_size(d->dtype);
+  if (!elt || elt > 2) return fail(EQB_ERR_UNSUPPORTED, "static maps: uint8 / fp16 / bf16 images");
+  if (d->channels != 1 && d->channels != 3 && d->channels != 4)
+    return fail(EQB_ERR_UNSUPPORTED, "static maps: 1, 3 or 4 channels");
+  if (d->src_w > 65536 || d->src_h > 65536)
+    return fail(EQB_ERR_UNSUPPORTED, "static maps: source sides up to 65536");
+  for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
+  for (int m = 0; m < kTmaBoxes; ++m) {
+    p.tma_bw[m] = box_w(elt, m);
+    p.tma_bh[m] = lean_box_h(elt, m, d->channels);
+  }
+  return EQB_OK;
+}
+
+int32_t eqb_map_build(const eqb_remap_desc* d, const float* coords, void* map, void* heads,
+                      void* stream) {
+  Params p;
+  int rc = fill(d, false, p);
+  if (rc != EQB_OK) return rc;
+  if (!coords || !map || !heads) return fail(EQB_ERR_INVALID, "null argument");
+  rc = map_box_table(d, p);
+  if (rc != EQB_OK) return rc;
+  const cudaError_t e = launch_map_pack(p, coords, map, heads, (int)elt_size(d->dtype),
+                                        static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(EQB_ERR_CUDA, "map build launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  g_err[0] = 0;
+  return EQB_OK;
+}
+
+int32_t eqb_remap_mapped(const eqb_remap_desc* d, const void* map, const void* heads,
+                         void* stream) {
+  Params p;
+  int rc = fill(d, true, p);
+  if (rc != EQB_OK) return rc;
+  if (!map || !heads) return fail(EQB_ERR_INVALID, "null argument");
+  rc = map_box_table(d, p);
+  if (rc != EQB_OK) return rc;
+  if (d->mode != EQB_BILINEAR || d->clip || (d->flags & EQB_FLAG_CHANNELS_LAST))
+    return fail(EQB_ERR_UNSUPPORTED, "static maps: bilinear, planar, no clamp");
+  const long long per16 = 16 / (long long)elt_size(d->dtype);
+  if (reinterpret_cast<uintptr_t>(d->src) % 16 || d->src_stride_b % per16 ||
+      d->src_stride_c % per16 || d->src_stride_h % per16 || d->src_w < 4 || d->src_h < 4)
+    return fail(EQB_ERR_UNSUPPORTED, "static maps: 16-byte aligned source rows and planes");
+  if (!dst_vector_ok(d, 4) || d->dst_w % 4)
+    return fail(EQB_ERR_UNSUPPORTED, "static maps: 4-pixel aligned destination rows");
+  setup_tma(d, p, true);
+  if (!p.use_tma) return fail(EQB_ERR_UNSUPPORTED, "static maps: no tensor-map encoder");
+  const cudaError_t e = launch_mapped(p, d->dtype, map, heads, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(EQB_ERR_CUDA, "mapped remap launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  g_err[0] = 0;
+  return EQB_OK;
+}
+
 int32_t eqb_remap_coords(const eqb_remap_desc* d, float* coords_out, void* stream) {
   Params p;
   const int rc = fill(d, false, p);

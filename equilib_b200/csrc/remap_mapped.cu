@@ -1,0 +1,241 @@
+// Static-camera path: the sampling map of a fixed set of rotations is built
+// once -- per output pixel the top-left tap (x, y) and the two bilinear fractions, 8 bytes;
+// per 64 x 8 tile the shared-memory box its footprint fits -- and every later frame is
+// remapped from it: no ray, no asin / atan2, no interpolation, no bounding box.  The
+// reference's counterpart is its grid cache (equilib/_cache.py:21-40), which keeps the
+// rays but recomputes rotation, spherical mapping and normalisation every call; its
+// README.md:168 lists the full-map cache as future work.
+//
+//   eqb_map_build   coordinates (eqb_remap_coords output) -> map + tile headers
+//   eqb_remap_mapped   frames + map -> frames   (bilinear, 1 / 3 / 4 planar channels of
+//                      1- or 2-byte pixels, the lean kernel's blend)
+#include "remap_kernels.cuh"
+
+namespace eqb {
+
+constexpr unsigned kFracOne = 65535u;  // fractions are stored as round(f * 65535)
+
+// ---- build -------------------------------------------------------------------------
+// One CTA per 64 x 8 tile, lanes laid out as in the lean kernel (16 x 2 lanes per warp, a
+// lane owns 4 consecutive pixels).  Coordinates go through the same to_index / floor /
+// footprint shift as the remap kernels, so the taps are the ones the exact path uses.
+__global__ void __launch_bounds__(kLeanWarps * 32)
+    map_pack_kernel(const __grid_constant__ Params p, const float* __restrict__ coords,
+                    uint2* __restrict__ map, int4* __restrict__ heads, int per16) {
+  __shared__ int bbox[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lx = lane % kStLaneW, ly = lane / kStLaneW;
+  const int b = blockIdx.z;
+  const int yq = blockIdx.y * kLeanTileH + warp * kStLaneH + ly;
+  const int x0 = blockIdx.x * 64 + lx * 4;
+  if (tid == 0) { bbox[0] = 0x7fffffff; bbox[1] = 0x7fffffff; bbox[2] = -1; bbox[3] = -1; }
+  __syncthreads();
+  int nx = 0x7fffffff, ny = 0x7fffffff, mx = -1, my = -1;
+  if (yq < p.dh) {
+    const long long plane = (long long)p.dh * p.dw;
+    const float* cj = coords + (long long)b * 2 * plane + (long long)yq * p.dw;
+    const float* ci = cj + plane;
+    uint2* mrow = map + ((long long)b * p.dh + yq) * p.dw;
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + i;
+      if (x >= p.dw) break;
+      const float ix = to_index(__ldg(ci + x), p.inv_wm1, p.swm1f);
+      const float iy = to_index(__ldg(cj + x), p.inv_hm1, p.shm1f);
+      const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
+      const float fx = __fsub_rn(ix, xf), fy = __fsub_rn(iy, yf);
+      const int xi = (int)xf, yi = (int)yf;
+      const unsigned qx = (unsigned)__float2int_rn(fx * (float)kFracOne);
+      const unsigned qy = (unsigned)__float2int_rn(fy * (float)kFracOne);
+      mrow[x] = make_uint2((unsigned)xi | ((unsigned)yi << 16), qx | (qy << 16));
+      nx = min(nx, xi); ny = min(ny, yi); mx = max(mx, xi); my = max(my, yi);
+    }
+  }
+  nx = __reduce_min_sync(0xffffffffu, nx);
+  ny = __reduce_min_sync(0xffffffffu, ny);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  my = __reduce_max_sync(0xffffffffu, my);
+  if (lane == 0) {
+    atomicMin(&bbox[0], nx); atomicMin(&bbox[1], ny);
+    atomicMax(&bbox[2], mx); atomicMax(&bbox[3], my);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // the footprint is exact here (every tap is known): no margin
+    const int gx0 = bbox[0] & ~(per16 - 1), gy0 = bbox[1];
+    const int need_w = bbox[2] + 2 - gx0, need_h = bbox[3] + 2 - gy0;
+    int m = -1;
+    if (bbox[2] >= 0 && bbox[2] - bbox[0] < (p.sw >> 1))
+      for (int k = kTmaBoxes - 1; k >= 0; --k)
+        if (need_w <= p.tma_bw[k] && need_h <= p.tma_bh[k]) m = k;
+    const long long tile =
+        ((long long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    heads[tile] = make_int4(gx0, gy0, m, 0);
+  }
+}
+
+// ---- remap from the map ------------------------------------------------------------------
+template <typename T, int NC>
+__global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
+    remap_mapped_kernel(const __grid_constant__ Params p, const uint2* __restrict__ map,
+                        const int4* __restrict__ heads, int tiles_x) {
+  constexpr int PX = 4;
+  constexpr int ELT = (int)sizeof(T);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long tma_bar;
+  unsigned tma_phase = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) mbar_init(&tma_bar, 1);
+  __syncthreads();
+  const int lx = lane % kStLaneW, ly = lane / kStLaneW;
+  const int b = blockIdx.z;
+  const int yq = blockIdx.y * kLeanTileH + warp * kStLaneH + ly;
+  const int y = min(yq, p.dh - 1);
+  const unsigned tile_s = smem_u32(smem_raw);
+  const T* const src_b = static_cast<const T*>(p.src) + (long long)b * p.ssb;
+  T* const dst_row = static_cast<T*>(p.dst) + (long long)b * p.dsb + (long long)y * p.dsh;
+  const uint2* const map_row = map + ((long long)b * p.dh + y) * p.dw;
+  const int4* const head_row = heads + ((long long)b * gridDim.y + blockIdx.y) * tiles_x;
+  const int ssh = (int)p.ssh;
+  const float q = 1.0f / (float)kFracOne;
+
+  for (int it = 0; it < p.iters; ++it) {
+    const int tx = blockIdx.x * p.iters + it;
+    if (tx >= tiles_x) break;  // uniform
+    const int x0 = tx * 64 + lx * PX;
+    const bool live = yq < p.dh && x0 < p.dw;
+    const int4 hd = __ldg(head_row + tx);
+    const int gx0 = hd.x, gy0 = hd.y, m = hd.z;
+    const bool boxed = m >= 0;
+    const int pitch = p.tma_bw[boxed ? m : 0], box_h = p.tma_bh[boxed ? m : 0];
+    __syncthreads();  // every warp is done reading the previous tile's box
+    if (boxed && tid == 0) {
+      mbar_expect_tx(&tma_bar, (unsigned)(pitch * box_h * NC * ELT));
+      tma_load_box(smem_raw, &p.tmaps[m], &tma_bar, gx0, gy0, 0, p.tma_batched ? b : 0);
+    }
+    unsigned a[PX];
+    float fx[PX], fy[PX];
+    {
+      uint2 e[PX];
+      if (live && x0 + PX <= p.dw) {
+        const uint4 e01 = __ldg(reinterpret_cast<const uint4*>(map_row + x0));
+        const uint4 e23 = __ldg(reinterpret_cast<const uint4*>(map_row + x0) + 1);
+        e[0] = make_uint2(e01.x, e01.y); e[1] = make_uint2(e01.z, e01.w);
+        e[2] = make_uint2(e23.x, e23.y); e[3] = make_uint2(e23.z, e23.w);
+      } else {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) e[i] = __ldg(map_row + min(x0 + i, p.dw - 1));
+      }
+#pragma unroll
+      for (int i = 0; i < PX; ++i) {
+        const int xi = (int)(e[i].x & 0xffffu), yi = (int)(e[i].x >> 16);
+        fx[i] = (float)(e[i].y & 0xffffu) * q;
+        fy[i] = (float)(e[i].y >> 16) * q;
+        a[i] = boxed ? tile_s + (unsigned)(((yi - gy0) * pitch + (xi - gx0)) * ELT)
+                     : (unsigned)(yi * ssh + xi);
+      }
+    }
+    if (boxed) {
+      mbar_wait(&tma_bar, tma_phase);
+      tma_phase ^= 1u;
+    }
+    if (!live) continue;
+    T* dst = dst_row + x0;
+    const int npx = min(PX, p.dw - x0);
+    if (boxed && npx == PX) {
+      switch (m) {
+        case 0: lean_blend<T, 0, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 1: lean_blend<T, 1, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 2: lean_blend<T, 2, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 3: lean_blend<T, 3, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 4: lean_blend<T, 4, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 5: lean_blend<T, 5, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 6: lean_blend<T, 6, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 7: lean_blend<T, 7, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 8: lean_blend<T, 8, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 9: lean_blend<T, 9, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 10: lean_blend<T, 10, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        default: lean_blend<T, 11, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+      }
+      continue;
+    }
+    // ragged right edge (taps from the box, element loads) or no box (global gathers)
+    float w_nw[PX], w_ne[PX], w_sw[PX], w_se[PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      const float ax = __fsub_rn(1.0f, fx[i]), ay = __fsub_rn(1.0f, fy[i]);
+      w_nw[i] = __fmul_rn(ax, ay);
+      w_ne[i] = __fmul_rn(fx[i], ay);
+      w_sw[i] = __fmul_rn(ax, fy[i]);
+      w_se[i] = __fmul_rn(fx[i], fy[i]);
+    }
+    const T* src = src_b;
+    const T* sm = reinterpret_cast<const T*>(smem_raw);
+    for (int c = 0; c < NC; ++c, src += p.ssc, sm += pitch * box_h) {
+      float o[PX];
+#pragma unroll
+      for (int i = 0; i < PX; ++i) {
+        o[i] = 0.0f;
+        if (i >= npx) continue;
+        if (boxed) {
+          const T* q0 = sm + (a[i] - tile_s) / ELT;
+          const T* q1 = q0 + pitch;
+          o[i] = blend4(lds_f(q0), lds_f(q0 + 1), lds_f(q1), lds_f(q1 + 1), w_nw[i], w_ne[i],
+                        w_sw[i], w_se[i]);
+        } else {
+          const T* q0 = src + (int)a[i];
+          float v_nw, v_ne, v_sw, v_se;
+          ldg_pair<T>(q0, v_nw, v_ne);
+          ldg_pair<T>(q0 + ssh, v_sw, v_se);
+          o[i] = blend4(v_nw, v_ne, v_sw, v_se, w_nw[i], w_ne[i], w_sw[i], w_se[i]);
+        }
+      }
+      emit<T, PX>(dst + c * p.dsc, o, npx, p.flags);
+    }
+  }
+}
+
+cudaError_t launch_map_pack(const Params& p, const float* coords, void* map, void* heads,
+                            int elt, cudaStream_t stream) {
+  const dim3 grid((unsigned)((p.dw + 63) / 64), (unsigned)((p.dh + kLeanTileH - 1) / kLeanTileH),
+                  (unsigned)p.B);
+  map_pack_kernel<<<grid, kLeanWarps * 32, 0, stream>>>(
+      p, coords, static_cast<uint2*>(map), static_cast<int4*>(heads), 16 / elt);
+  return cudaGetLastError();
+}
+
+template <typename T, int NC>
+static cudaError_t launch_mapped_nc(Params p, const void* map, const void* heads,
+                                    cudaStream_t stream) {
+  const int tiles_x = (p.dw + 63) / 64;
+  const long long tiles_y = (p.dh + kLeanTileH - 1) / kLeanTileH;
+  const long long tiles = tiles_x * tiles_y * p.B;
+  const long long wave = 148ll * 2048 / (kLeanWarps * 32);
+  p.iters = tiles >= wave * 8 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
+  const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
+  remap_mapped_kernel<T, NC><<<grid, kLeanWarps * 32, lean_smem_bytes(), stream>>>(
+      p, static_cast<const uint2*>(map), static_cast<const int4*>(heads), tiles_x);
+  return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_mapped_t(const Params& p, const void* map, const void* heads,
+                                   cudaStream_t stream) {
+  switch (p.C) {
+    case 1: return launch_mapped_nc<T, 1>(p, map, heads, stream);
+    case 3: return launch_mapped_nc<T, 3>(p, map, heads, stream);
+    case 4: return launch_mapped_nc<T, 4>(p, map, heads, stream);
+  }
+  return cudaErrorNotSupported;
+}
+
+cudaError_t launch_mapped(const Params& p, int dtype, const void* map, const void* heads,
+                          cudaStream_t stream) {
+  switch (dtype) {
+    case EQB_U8: return launch_mapped_t<uint8_t>(p, map, heads, stream);
+    case EQB_F16: return launch_mapped_t<__half>(p, map, heads, stream);
+    case EQB_BF16: return launch_mapped_t<__nv_bfloat16>(p, map, heads, stream);
+  }
+  return cudaErrorNotSupported;
+}
+
+}  // namespace eqb

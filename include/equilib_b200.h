@@ -167,6 +167,30 @@ int32_t eqb_remap(const eqb_remap_desc* desc, void* stream);
 int32_t eqb_remap_supports_channels_last(const eqb_remap_desc* desc);
 
 /*
+ * Static-camera path (the reference's roadmap item "full-grid cache for the
+ * fixed-rotation case", README.md:168; its equilib/_cache.py:21-40 caches the rays only).
+ *
+ * eqb_map_build packs coordinates -- the output of eqb_remap_coords for the same
+ * descriptor -- into a sampling map: per output pixel 8 bytes (top-left tap x | y << 16,
+ * bilinear fractions as round(f * 65535) x | y << 16) in `map` (batch x dst_h x dst_w
+ * entries) and per EQB_MAP_TILE_W x EQB_MAP_TILE_H output tile 16 bytes in `heads`
+ * (batch x ceil(dst_h / TILE_H) x ceil(dst_w / TILE_W) entries: origin and shape index of
+ * the shared-memory box the tile's footprint fits, or -1).  desc->dtype and
+ * desc->channels select the box table; src / dst are not touched.
+ *
+ * eqb_remap_mapped remaps desc->src into desc->dst from such a map: bilinear, planar
+ * 1 / 3 / 4 channels of uint8 / fp16 / bf16, no clamp, 16-byte aligned source rows, 4-pixel
+ * aligned destination rows (EQB_ERR_UNSUPPORTED otherwise).  Results equal eqb_remap with
+ * EQB_FLAG_EXACT_COORDS up to the 16-bit fractions.
+ */
+#define EQB_MAP_TILE_W 64
+#define EQB_MAP_TILE_H 8
+int32_t eqb_map_build(const eqb_remap_desc* desc, const float* coords, void* map, void* heads,
+                      void* stream);
+int32_t eqb_remap_mapped(const eqb_remap_desc* desc, const void* map, const void* heads,
+                         void* stream);
+
+/*
  * Writes the sampling coordinates of the transform (what the reference calls
  * the grid: B x 2 x dst_h x dst_w fp32, (uj, ui) in source pixel units, before
  * the sampler's normalisation) to `coords_out`.  src/dst/dtype are ignored.

@@ -808,3 +808,37 @@ def test_lean_kernel_random_rotations_match_the_exact_path():
         a = equilib_b200.equi2equi(u8, rots).int()
         b = equilib_b200.equi2equi(u8, rots, fast_coords=False).int()
         assert float(((a - b).abs() <= 1).float().mean()) >= 0.9999
+
+
+# --- static-camera map ----------------------------------------------------
+
+
+@pytest.mark.parametrize("dtype,channels", [(torch.bfloat16, 3), (torch.uint8, 4),
+                                            (torch.float16, 1)])
+def test_static_remap_equals_the_exact_path(dtype, channels):
+    """A map built once for fixed rotations gives what the exact-coordinate call gives,
+    up to its 16-bit bilinear fractions (1.5e-5 of a pixel)."""
+    shape = (3, channels, 512, 1024)
+    img = torch.from_numpy(cases.band_limited_image(shape, "float32", px=96, py=64))
+    img = (img * 255).to(torch.uint8) if dtype == torch.uint8 else img.to(dtype)
+    img = img.to(DEV)
+    rots = HARD_ROTS[1:4]  # includes a pole-up view (tiles that fit no box)
+    sr = equilib_b200.StaticRemap.equi2equi(rots, img.shape, dtype, DEV, height=520, width=1012)
+    n0 = _lib.lib().eqb_launch_count()
+    out = sr(img)
+    assert _lib.lib().eqb_launch_count() == n0 + 1  # one kernel per frame batch
+    ref = equilib_b200.equi2equi(img, rots, height=520, width=1012, fast_coords=False)
+    d = (out.float() - ref.float()).abs()
+    tol = 1.0 if dtype == torch.uint8 else (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10)
+    assert float((d <= tol * 1.01).float().mean()) >= 0.9999
+    assert float((d == 0).float().mean()) >= 0.995
+    # a second batch through the same map
+    img2 = img.flip(3).contiguous()
+    assert torch.equal(sr(img2), sr(img2.clone()))
+    # perspective views of the same frames
+    sp = equilib_b200.StaticRemap.equi2pers(rots, img.shape, dtype, DEV, 512, 768, 100.0)
+    ref_p = equilib_b200.equi2pers(img, rots, 512, 768, 100.0, fast_coords=False)
+    dp = (sp(img).float() - ref_p.float()).abs()
+    assert float((dp <= tol * 1.01).float().mean()) >= 0.9999
+    with pytest.raises(ValueError):
+        sr(img[:2])

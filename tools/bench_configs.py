@@ -13,6 +13,7 @@ import json
 import math
 import os
 import sys
+import time
 
 import torch
 
@@ -62,7 +63,6 @@ def main():
     ms = timed(lambda: op(equi[0], rot), steps=50, warmup=5)
     report("1: equi2pers fp32 4K -> 480x640 (device time per call, back to back)", ms, 480 * 640,
            480 * 640 * 3 * 4 * 2, note="latency-bound; includes host dispatch when it dominates")
-    import time
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(200):
@@ -131,6 +131,22 @@ def main():
         report(f"N1: equi2equi uint8 b32 4K bilinear, {c} channels, channels-last", ms, px,
                2 * px * c)
         del src, src_cl
+
+    # static camera -- the sampling map of fixed rotations built once (8 B/px),
+    # then applied per batch of frames; "alg bytes" here include the map read
+    for dtype in (torch.bfloat16, torch.uint8):
+        src = frames(32, 3, 2048, 4096, dtype)
+        r = rots(32)
+        px = 32 * 2048 * 4096
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sr = equilib_b200.StaticRemap.equi2equi(r, src.shape, dtype, DEV)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3
+        ms = timed(lambda: sr(src))
+        report(f"N3: equi2equi {str(dtype)[6:]} b32 4K bilinear through a static map", ms, px,
+               2 * px * 3 * src.element_size() + 8 * px, map_build_ms=round(build_ms, 2))
+        del src, sr
 
     # config 3: equi2cube + cube2equi, batch 16, w_face 1024, fp32 and uint8
     for dtype in (torch.float32, torch.uint8):
