@@ -42,6 +42,26 @@ def test_descriptor_validation_without_gpu():
     assert b"transform" in L.eqb_last_error()
 
 
+def test_new_entry_points_validate_without_gpu():
+    """Channels-last probe and the static-map entry points reject bad descriptors on the
+    host, before any launch."""
+    L = _lib.lib()
+    d = _lib.RemapDesc()
+    assert L.eqb_remap_supports_channels_last(ctypes.byref(d)) == 0
+    assert L.eqb_remap_supports_channels_last(None) == 0
+    assert L.eqb_last_error() == b""  # a probe, not an error
+    assert L.eqb_map_build(ctypes.byref(d), None, None, None, None) == -1
+    assert L.eqb_remap_mapped(None, None, None, None) == -1
+    # a well-formed equi2equi descriptor whose image type the map path does not serve
+    d.transform, d.mode, d.dtype = _lib.EQUI2EQUI, 1, _lib.F32
+    d.batch, d.channels = 1, 3
+    d.src_h, d.src_w, d.dst_h, d.dst_w = 64, 128, 64, 128
+    d.mats = d.tab_x = d.tab_y = 16  # non-null (never dereferenced on the host)
+    rc = L.eqb_map_build(ctypes.byref(d), 16, 16, 16, None)
+    assert rc == -2 and b"static maps" in L.eqb_last_error()
+    assert (_lib.MAP_TILE_W, _lib.MAP_TILE_H) == (64, 8)
+
+
 def test_struct_layout_matches_header():
     # sizeof(eqb_remap_desc): 10 int32 + 2x(ptr + 3 int64) + 5 ptr + int64 + ptr
     #                         + 2 int32 + 12 int64 + ptr
