@@ -505,15 +505,29 @@ int32_t eqb_remap_mapped(const eqb_remap_desc* d, const void* map, const void* h
   if (!map || !heads) return fail(EQB_ERR_INVALID, "null argument");
   rc = map_box_table(d, p);
   if (rc != EQB_OK) return rc;
-  if (d->mode != EQB_BILINEAR || d->clip || (d->flags & EQB_FLAG_CHANNELS_LAST))
-    return fail(EQB_ERR_UNSUPPORTED, "static maps: bilinear, planar, no clamp");
-  const long long per16 = 16 / (long long)elt_size(d->dtype);
-  if (reinterpret_cast<uintptr_t>(d->src) % 16 || d->src_stride_b % per16 ||
-      d->src_stride_c % per16 || d->src_stride_h % per16 || d->src_w < 4 || d->src_h < 4)
-    return fail(EQB_ERR_UNSUPPORTED, "static maps: 16-byte aligned source rows and planes");
-  if (!dst_vector_ok(d, 4) || d->dst_w % 4)
-    return fail(EQB_ERR_UNSUPPORTED, "static maps: 4-pixel aligned destination rows");
-  setup_tma(d, p, true);
+  if (d->mode != EQB_BILINEAR || d->clip)
+    return fail(EQB_ERR_UNSUPPORTED, "static maps: bilinear, no clamp");
+  if (d->dst_w % 4) return fail(EQB_ERR_UNSUPPORTED, "static maps: output width % 4 == 0");
+  if (d->flags & EQB_FLAG_CHANNELS_LAST) {
+    // uint8 RGB / RGBX frames in the decoder's layout: the alignment rules of can_nhwc
+    const long long c = d->channels, va = c == 4 ? 16 : 4;
+    if (d->dtype != EQB_U8 || (c != 3 && c != 4) || d->src_stride_c != 1 || d->dst_stride_c != 1 ||
+        d->src_stride_h < c * d->src_w || d->dst_stride_h < c * d->dst_w ||
+        reinterpret_cast<uintptr_t>(d->src) % 16 || d->src_stride_h % 16 || d->src_stride_b % 16 ||
+        (c * d->src_w) % 4 || reinterpret_cast<uintptr_t>(d->dst) % va || d->dst_stride_h % va ||
+        d->dst_stride_b % va || d->src_w < 4 || d->src_h < 4)
+      return fail(EQB_ERR_UNSUPPORTED,
+                  "static maps, channels-last: uint8 RGB / RGBX with 16-byte aligned source rows");
+    setup_tma_nhwc(d, p);
+  } else {
+    const long long per16 = 16 / (long long)elt_size(d->dtype);
+    if (reinterpret_cast<uintptr_t>(d->src) % 16 || d->src_stride_b % per16 ||
+        d->src_stride_c % per16 || d->src_stride_h % per16 || d->src_w < 4 || d->src_h < 4)
+      return fail(EQB_ERR_UNSUPPORTED, "static maps: 16-byte aligned source rows and planes");
+    if (!dst_vector_ok(d, 4))
+      return fail(EQB_ERR_UNSUPPORTED, "static maps: 4-pixel aligned destination rows");
+    setup_tma(d, p, true);
+  }
   if (!p.use_tma) return fail(EQB_ERR_UNSUPPORTED, "static maps: no tensor-map encoder");
   const cudaError_t e = launch_mapped(p, d->dtype, map, heads, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)

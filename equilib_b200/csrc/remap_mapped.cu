@@ -74,12 +74,16 @@ __global__ void __launch_bounds__(kLeanWarps * 32)
 }
 
 // ---- remap from the map ------------------------------------------------------------------
-template <typename T, int NC>
+// IL = 0: NC planar channels.  IL = 3 / 4: channels-last uint8 RGB / RGBX (NC == IL), the
+// layout of decoded video frames, read and written in place (see nhwc_blend).
+template <typename T, int NC, int IL = 0>
 __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
     remap_mapped_kernel(const __grid_constant__ Params p, const uint2* __restrict__ map,
                         const int4* __restrict__ heads, int tiles_x) {
   constexpr int PX = 4;
   constexpr int ELT = (int)sizeof(T);
+  constexpr int PXE = IL ? IL : 1;  // elements from a pixel to its right neighbour
+  static_assert(IL == 0 || (ELT == 1 && NC == IL), "channels-last: uint8 RGB / RGBX");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long tma_bar;
   unsigned tma_phase = 0;
@@ -110,7 +114,9 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
     __syncthreads();  // every warp is done reading the previous tile's box
     if (boxed && tid == 0) {
       mbar_expect_tx(&tma_bar, (unsigned)(pitch * box_h * NC * ELT));
-      tma_load_box(smem_raw, &p.tmaps[m], &tma_bar, gx0, gy0, 0, p.tma_batched ? b : 0);
+      // (channels-last maps are rows of 32-bit words)
+      tma_load_box(smem_raw, &p.tmaps[m], &tma_bar, IL ? gx0 * IL / 4 : gx0, gy0, 0,
+                   p.tma_batched ? b : 0);
     }
     unsigned a[PX];
     float fx[PX], fy[PX];
@@ -130,8 +136,8 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
         const int xi = (int)(e[i].x & 0xffffu), yi = (int)(e[i].x >> 16);
         fx[i] = (float)(e[i].y & 0xffffu) * q;
         fy[i] = (float)(e[i].y >> 16) * q;
-        a[i] = boxed ? tile_s + (unsigned)(((yi - gy0) * pitch + (xi - gx0)) * ELT)
-                     : (unsigned)(yi * ssh + xi);
+        a[i] = boxed ? tile_s + (unsigned)(((yi - gy0) * pitch + (xi - gx0)) * (PXE * ELT))
+                     : (unsigned)(yi * ssh + xi * PXE);
       }
     }
     if (boxed) {
@@ -139,22 +145,27 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
       tma_phase ^= 1u;
     }
     if (!live) continue;
-    T* dst = dst_row + x0;
+    T* dst = dst_row + x0 * PXE;
     const int npx = min(PX, p.dw - x0);
     if (boxed && npx == PX) {
+      auto blend_m = [&](auto mc) {
+        constexpr int M = decltype(mc)::value;
+        if constexpr (IL != 0) nhwc_blend<IL, M>(a, fx, fy, dst, p.flags);
+        else lean_blend<T, M, NC>(a, fx, fy, dst, p.dsc, p.flags);
+      };
       switch (m) {
-        case 0: lean_blend<T, 0, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 1: lean_blend<T, 1, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 2: lean_blend<T, 2, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 3: lean_blend<T, 3, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 4: lean_blend<T, 4, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 5: lean_blend<T, 5, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 6: lean_blend<T, 6, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 7: lean_blend<T, 7, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 8: lean_blend<T, 8, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 9: lean_blend<T, 9, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        case 10: lean_blend<T, 10, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
-        default: lean_blend<T, 11, NC>(a, fx, fy, dst, p.dsc, p.flags); break;
+        case 0: blend_m(cuda::std::integral_constant<int, 0>{}); break;
+        case 1: blend_m(cuda::std::integral_constant<int, 1>{}); break;
+        case 2: blend_m(cuda::std::integral_constant<int, 2>{}); break;
+        case 3: blend_m(cuda::std::integral_constant<int, 3>{}); break;
+        case 4: blend_m(cuda::std::integral_constant<int, 4>{}); break;
+        case 5: blend_m(cuda::std::integral_constant<int, 5>{}); break;
+        case 6: blend_m(cuda::std::integral_constant<int, 6>{}); break;
+        case 7: blend_m(cuda::std::integral_constant<int, 7>{}); break;
+        case 8: blend_m(cuda::std::integral_constant<int, 8>{}); break;
+        case 9: blend_m(cuda::std::integral_constant<int, 9>{}); break;
+        case 10: blend_m(cuda::std::integral_constant<int, 10>{}); break;
+        default: blend_m(cuda::std::integral_constant<int, 11>{}); break;
       }
       continue;
     }
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
     }
     const T* src = src_b;
     const T* sm = reinterpret_cast<const T*>(smem_raw);
-    for (int c = 0; c < NC; ++c, src += p.ssc, sm += pitch * box_h) {
+    for (int c = 0; c < NC; ++c, src += (IL ? 1 : p.ssc), sm += (IL ? 1 : pitch * box_h)) {
       float o[PX];
 #pragma unroll
       for (int i = 0; i < PX; ++i) {
@@ -178,18 +189,31 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
         if (i >= npx) continue;
         if (boxed) {
           const T* q0 = sm + (a[i] - tile_s) / ELT;
-          const T* q1 = q0 + pitch;
-          o[i] = blend4(lds_f(q0), lds_f(q0 + 1), lds_f(q1), lds_f(q1 + 1), w_nw[i], w_ne[i],
-                        w_sw[i], w_se[i]);
-        } else {
+          const T* q1 = q0 + pitch * PXE;
+          o[i] = blend4(lds_f(q0), lds_f(q0 + PXE), lds_f(q1), lds_f(q1 + PXE), w_nw[i],
+                        w_ne[i], w_sw[i], w_se[i]);
+        } else if (IL == 0) {
           const T* q0 = src + (int)a[i];
           float v_nw, v_ne, v_sw, v_se;
           ldg_pair<T>(q0, v_nw, v_ne);
           ldg_pair<T>(q0 + ssh, v_sw, v_se);
           o[i] = blend4(v_nw, v_ne, v_sw, v_se, w_nw[i], w_ne[i], w_sw[i], w_se[i]);
+        } else {
+          const T* q0 = src + (int)a[i];
+          const T* q1 = q0 + ssh;
+          o[i] = blend4(ld_f(q0), ld_f(q0 + PXE), ld_f(q1), ld_f(q1 + PXE), w_nw[i], w_ne[i],
+                        w_sw[i], w_se[i]);
         }
       }
-      emit<T, PX>(dst + c * p.dsc, o, npx, p.flags);
+      if (IL) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+          const T v = OutCvt<T>::cvt(o[i], p.flags);
+          if (i < npx) Pack<T, 1>::st(dst + i * PXE + c, &v);
+        }
+      } else {
+        emit<T, PX>(dst + c * p.dsc, o, npx, p.flags);
+      }
     }
   }
 }
@@ -203,7 +227,7 @@ cudaError_t launch_map_pack(const Params& p, const float* coords, void* map, voi
   return cudaGetLastError();
 }
 
-template <typename T, int NC>
+template <typename T, int NC, int IL = 0>
 static cudaError_t launch_mapped_nc(Params p, const void* map, const void* heads,
                                     cudaStream_t stream) {
   const int tiles_x = (p.dw + 63) / 64;
@@ -212,7 +236,8 @@ static cudaError_t launch_mapped_nc(Params p, const void* map, const void* heads
   const long long wave = 148ll * 2048 / (kLeanWarps * 32);
   p.iters = tiles >= wave * 8 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
-  remap_mapped_kernel<T, NC><<<grid, kLeanWarps * 32, lean_smem_bytes(), stream>>>(
+  // (+16: the channels-last RGB tap loads are aligned words that may end past the last tap)
+  remap_mapped_kernel<T, NC, IL><<<grid, kLeanWarps * 32, lean_smem_bytes() + 16, stream>>>(
       p, static_cast<const uint2*>(map), static_cast<const int4*>(heads), tiles_x);
   return cudaGetLastError();
 }
@@ -230,6 +255,11 @@ static cudaError_t launch_mapped_t(const Params& p, const void* map, const void*
 
 cudaError_t launch_mapped(const Params& p, int dtype, const void* map, const void* heads,
                           cudaStream_t stream) {
+  if (p.flags & EQB_FLAG_CHANNELS_LAST) {
+    if (dtype == EQB_U8 && p.C == 3) return launch_mapped_nc<uint8_t, 3, 3>(p, map, heads, stream);
+    if (dtype == EQB_U8 && p.C == 4) return launch_mapped_nc<uint8_t, 4, 4>(p, map, heads, stream);
+    return cudaErrorNotSupported;
+  }
   switch (dtype) {
     case EQB_U8: return launch_mapped_t<uint8_t>(p, map, heads, stream);
     case EQB_F16: return launch_mapped_t<__half>(p, map, heads, stream);

@@ -13,7 +13,8 @@ chain -- the kernel reads the map, loads the box with TMA and blends.
     out = sr(frames)            # same result as equi2equi(frames, rots, fast_coords=False)
                                 # up to the 16-bit fractions of the map
 
-Bilinear only; 1, 3 or 4 planar channels of uint8 / float16 / bfloat16.
+Bilinear only; 1, 3 or 4 planar channels of uint8 / float16 / bfloat16, or uint8 RGB / RGBX
+frames in torch.channels_last.
 """
 
 from __future__ import annotations
@@ -83,12 +84,21 @@ class StaticRemap:
             raise ValueError(
                 f"StaticRemap was built for {self.src_shape} {self.dtype} on {self.device}, got "
                 f"{tuple(src.shape)} {src.dtype} on {src.device}")
-        if src.stride(3) != 1:
-            src = src.contiguous()
         b, c = self.src_shape[:2]
+        flags = _lib.FLAG_SATURATE_U8 if (saturate_uint8 and src.dtype == torch.uint8) else 0
+        # uint8 RGB / RGBX frames in torch.channels_last (the decoder's layout) are read and
+        # written in place, like in equi2equi / equi2pers
+        cl = src.stride(3) != 1 and K.is_channels_last_u8(src) and src.stride(2) % 16 == 0 \
+            and src.data_ptr() % 16 == 0
+        if cl:
+            flags |= _lib.FLAG_CHANNELS_LAST
+            if out is None:
+                out = torch.empty((b, c) + self.dst_hw, dtype=src.dtype, device=src.device,
+                                  memory_format=torch.channels_last)
+        elif src.stride(3) != 1:
+            src = src.contiguous()
         if out is None:
             out = torch.empty((b, c) + self.dst_hw, dtype=src.dtype, device=src.device)
-        flags = _lib.FLAG_SATURATE_U8 if (saturate_uint8 and src.dtype == torch.uint8) else 0
         _ops.remap_mapped(src, out, self.map, self.heads, self._mats, self._tab_x, self._tab_y,
                           None, self.transform, flags)
         return out

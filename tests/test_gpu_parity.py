@@ -842,3 +842,19 @@ def test_static_remap_equals_the_exact_path(dtype, channels):
     assert float((dp <= tol * 1.01).float().mean()) >= 0.9999
     with pytest.raises(ValueError):
         sr(img[:2])
+
+
+@pytest.mark.parametrize("channels", [3, 4])
+def test_static_remap_channels_last_uint8(channels):
+    """Decoder-layout frames through a static map: in place, same values as planar."""
+    shape = (2, channels, 512, 1024)
+    img = torch.from_numpy(cases.noise_image(shape, "uint8", 21)).to(DEV)
+    rots = HARD_ROTS[1:3]
+    sr = equilib_b200.StaticRemap.equi2equi(rots, shape, torch.uint8, DEV)
+    planar = sr(img)
+    out = sr(img.contiguous(memory_format=torch.channels_last))
+    assert out.is_contiguous(memory_format=torch.channels_last) and not out.is_contiguous()
+    assert torch.equal(out, planar)
+    ref = equilib_b200.equi2equi(img, rots, fast_coords=False)
+    d = (out.int() - ref.int()).abs()
+    assert int(d.max()) <= 1 and float((d == 0).float().mean()) >= 0.99

@@ -146,6 +146,12 @@ def main():
         ms = timed(lambda: sr(src))
         report(f"N3: equi2equi {str(dtype)[6:]} b32 4K bilinear through a static map", ms, px,
                2 * px * 3 * src.element_size() + 8 * px, map_build_ms=round(build_ms, 2))
+        if dtype == torch.uint8:
+            src_cl = src.contiguous(memory_format=torch.channels_last)
+            ms = timed(lambda: sr(src_cl))
+            report("N3+N1: equi2equi uint8 RGB b32 4K bilinear, channels-last frames through a "
+                   "static map", ms, px, 2 * px * 3 + 8 * px)
+            del src_cl
         del src, sr
 
     # config 3: equi2cube + cube2equi, batch 16, w_face 1024, fp32 and uint8
