@@ -71,7 +71,7 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 #define EQB_FLAG_FORCE_STAGE 128u /* experiments: staged kernel wherever it is legal           */
 #define EQB_FLAG_NO_TMA 64u       /* staged kernel: cp.async row chunks instead of TMA     */
 #define EQB_FLAG_NO_LEAN 1024u    /* experiments: generic staged kernel where the lean     \
-                                     3-channel variant would run                           */
+                                     variant would run                                     */
 #define EQB_FLAG_CHANNELS_LAST 2048u /* src and dst are channels-last (NHWC): channel stride  \
                                        1, pixel stride = channels; strides_h in elements.     \
                                        Served for uint8 RGB / RGBX bilinear equi2equi and     \
@@ -179,9 +179,11 @@ int32_t eqb_remap_supports_channels_last(const eqb_remap_desc* desc);
  * desc->channels select the box table; src / dst are not touched.
  *
  * eqb_remap_mapped remaps desc->src into desc->dst from such a map: bilinear, planar
- * 1 / 3 / 4 channels of uint8 / fp16 / bf16, no clamp, 16-byte aligned source rows, 4-pixel
- * aligned destination rows (EQB_ERR_UNSUPPORTED otherwise).  Results equal eqb_remap with
- * EQB_FLAG_EXACT_COORDS up to the 16-bit fractions.
+ * 1 / 3 / 4 channels of uint8 / fp16 / bf16 -- or, with EQB_FLAG_CHANNELS_LAST, uint8 RGB /
+ * RGBX frames in NHWC layout -- no clamp, 16-byte aligned source rows, 4-pixel aligned
+ * destination rows (EQB_ERR_UNSUPPORTED otherwise).  Results equal eqb_remap with
+ * EQB_FLAG_EXACT_COORDS up to the 16-bit fractions.  coords_out of eqb_remap_coords is also
+ * "used by the product path" here, once per set of rotations.
  */
 #define EQB_MAP_TILE_W 64
 #define EQB_MAP_TILE_H 8
@@ -194,7 +196,7 @@ int32_t eqb_remap_mapped(const eqb_remap_desc* desc, const void* map, const void
  * Writes the sampling coordinates of the transform (what the reference calls
  * the grid: B x 2 x dst_h x dst_w fp32, (uj, ui) in source pixel units, before
  * the sampler's normalisation) to `coords_out`.  src/dst/dtype are ignored.
- * For tests and debugging; not used by the product path.
+ * Input of eqb_map_build; otherwise for tests and debugging.
  */
 int32_t eqb_remap_coords(const eqb_remap_desc* desc, float* coords_out, void* stream);
 
