@@ -167,6 +167,8 @@ def flags_of(dtype: torch.dtype, opt: "Options") -> int:
         flags |= _lib.FLAG_FORCE_STAGE
     if os.environ.get("EQUILIB_B200_NO_LEAN") == "1":
         flags |= _lib.FLAG_NO_LEAN
+    if os.environ.get("EQUILIB_B200_NO_LEAN2") == "1":
+        flags |= _lib.FLAG_NO_LEAN2
     return flags
 
 

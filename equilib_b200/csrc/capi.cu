@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "remap_kernels.cuh"
+#include "remap_lean2.cuh"
 
 namespace eqb {
 
@@ -330,8 +331,79 @@ static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
   p.use_tma = 1;
 }
 
+// The strip-node kernel (remap_lean2.cuh): bilinear, planar 1 / 3 / 4 channels, no clamp,
+// equi2equi / equi2pers / equi2cube, TMA.  fp32 images run it with the exact chain on every
+// pixel unless EQB_FLAG_FAST_COORDS is set; 8/16-bit images interpolate between the strip's
+// nodes unless EQB_FLAG_EXACT_COORDS is set.
+static bool can_lean2(const eqb_remap_desc* d) {
+  if (d->flags & (EQB_FLAG_NO_STAGE | EQB_FLAG_NO_TMA | EQB_FLAG_NO_LEAN | EQB_FLAG_NO_LEAN2 |
+                  EQB_FLAG_CHANNELS_LAST))
+    return false;
+  if (d->transform > EQB_EQUI2CUBE || d->mode != EQB_BILINEAR || d->clip) return false;
+  if (d->channels != 1 && d->channels != 3 && d->channels != 4) return false;
+  if (!encode_tiled()) return false;
+  const long long elt = (long long)elt_size(d->dtype), per16 = 16 / elt;
+  if (reinterpret_cast<uintptr_t>(d->src) % 16) return false;
+  if (d->src_stride_b % per16 || d->src_stride_c % per16 || d->src_stride_h % per16) return false;
+  if (d->src_w > 65536 || d->src_h > 65536 || d->src_w < 16 || d->src_h < 16) return false;
+  if (elt == 1) {  // uint8 results leave as pixel pairs
+    if (reinterpret_cast<uintptr_t>(d->dst) % 2) return false;
+    if (d->dst_stride_b % 2 || d->dst_stride_c % 2 || d->dst_stride_h % 2) return false;
+  }
+  if (d->transform == EQB_EQUI2CUBE) {
+    if (d->w_face % 64) return false;  // a 64-pixel tile must not straddle two cells
+    for (int i = 0; i < d->n_cells; ++i)
+      if (d->cell_offset[i] % 2) return false;
+  }
+  return (long long)d->batch * d->dst_h * d->dst_w >= (1ll << 18);
+}
+
+static void setup_tma_l2(const eqb_remap_desc* d, Params& p) {
+  p.use_tma = 0;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return;
+  const int elt = (int)elt_size(d->dtype);
+  CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                           : d->dtype == EQB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                           : d->dtype == EQB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const bool batched = d->src_stride_b > 0 && d->batch > 1;
+  const cuuint64_t dims[4] = {(cuuint64_t)d->src_w, (cuuint64_t)d->src_h, (cuuint64_t)d->channels,
+                              (cuuint64_t)(batched ? d->batch : 1)};
+  const cuuint64_t row = (cuuint64_t)d->src_stride_h * elt;
+  const cuuint64_t cstride = d->channels > 1 ? (cuuint64_t)d->src_stride_c * elt : row * d->src_h;
+  const cuuint64_t strides[3] = {row, cstride,
+                                 batched ? (cuuint64_t)d->src_stride_b * elt
+                                         : cstride * d->channels};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0 || strides[i] % 16) return;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
+  for (int m = 0; m < kL2Boxes; ++m) {
+    const int bw = l2_box_w(elt, m), bh = l2_box_h(elt, d->channels, m);
+    if (bw > 256 || bh < 12) continue;
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)d->channels, 1};
+    if (enc(&p.tmaps[m], dt, 4, const_cast<void*>(d->src), dims, strides, box, ones,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return;
+    p.tma_bw[m] = bw;
+    p.tma_bh[m] = bh;
+  }
+  p.tma_batched = batched ? 1 : 0;
+  p.use_tma = 1;
+}
+
 template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int px,
                                         cudaStream_t s) {
+  if (can_lean2(d)) {
+    setup_tma_l2(d, p);
+    if (p.use_tma) {
+      const bool exact = (d->flags & EQB_FLAG_EXACT_COORDS) ||
+                         (d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS));
+      return launch_lean2<XF>(p, d->dtype, exact, s);
+    }
+  }
   if (d->flags & EQB_FLAG_CHANNELS_LAST) {
     // (eqb_remap has checked can_nhwc)
     setup_tma_nhwc(d, p);

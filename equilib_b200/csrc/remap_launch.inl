@@ -2,6 +2,9 @@
 // transform and its mode/dtype/PX/warp-shape dispatch (one translation unit per
 // transform so the six compile in parallel).
 #include "remap_kernels.cuh"
+#if EQB_XF <= 2
+#include "remap_lean2.cuh"
+#endif
 
 namespace eqb {
 
@@ -173,6 +176,53 @@ cudaError_t launch_nhwc<EQB_XF>(const Params& p, cudaStream_t stream) {
 #if EQB_XF <= 1  // equi2equi, equi2pers
   if (p.C == 4) return launch_nhwc_il<EQB_XF, 4>(p, stream);
   if (p.C == 3) return launch_nhwc_il<EQB_XF, 3>(p, stream);
+#endif
+  return cudaErrorNotSupported;
+}
+
+// ---- remap_lean2_kernel (remap_lean2.cuh) ---------------------------------------------------
+#if EQB_XF <= 2
+template <int XF, typename T, int NC, bool EXACT>
+static cudaError_t launch_lean2_one(Params p, cudaStream_t stream) {
+  const long long tiles_x = (p.dw + kL2TileW - 1) / kL2TileW;
+  const long long tiles_y = (p.dh + kL2TileH - 1) / kL2TileH;
+  // tiles per strip: as many as leave >= 4 waves of CTAs (the node prologue amortises over
+  // the strip); a strip must not straddle two cube cells
+  const long long wave = 148ll * 8;
+  int iters = kL2MaxIters;
+  while (iters > 1 && ((tiles_x + iters - 1) / iters) * tiles_y * p.B < 4 * wave) iters >>= 1;
+  if (XF == EQB_EQUI2CUBE)
+    while (iters > 1 && p.w_face % (iters * kL2TileW)) iters >>= 1;
+  p.iters = iters;
+  const dim3 grid((unsigned)((tiles_x + iters - 1) / iters), (unsigned)tiles_y, (unsigned)p.B);
+  remap_lean2_kernel<XF, T, NC, EXACT>
+      <<<grid, kL2Warps * 32, l2_smem_bytes((int)sizeof(T)), stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int XF, typename T>
+static cudaError_t launch_lean2_t(const Params& p, bool exact, cudaStream_t stream) {
+  switch (p.C * 2 + (exact ? 1 : 0)) {
+    case 2: return launch_lean2_one<XF, T, 1, false>(p, stream);
+    case 3: return launch_lean2_one<XF, T, 1, true>(p, stream);
+    case 6: return launch_lean2_one<XF, T, 3, false>(p, stream);
+    case 7: return launch_lean2_one<XF, T, 3, true>(p, stream);
+    case 8: return launch_lean2_one<XF, T, 4, false>(p, stream);
+    case 9: return launch_lean2_one<XF, T, 4, true>(p, stream);
+  }
+  return cudaErrorNotSupported;  // (capi.cu::can_lean2)
+}
+#endif
+
+template <>
+cudaError_t launch_lean2<EQB_XF>(const Params& p, int dtype, bool exact, cudaStream_t stream) {
+#if EQB_XF <= 2
+  switch (dtype) {
+    case EQB_U8: return launch_lean2_t<EQB_XF, uint8_t>(p, exact, stream);
+    case EQB_F16: return launch_lean2_t<EQB_XF, __half>(p, exact, stream);
+    case EQB_BF16: return launch_lean2_t<EQB_XF, __nv_bfloat16>(p, exact, stream);
+    case EQB_F32: return launch_lean2_t<EQB_XF, float>(p, exact, stream);
+  }
 #endif
   return cudaErrorNotSupported;
 }

@@ -72,6 +72,8 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
 #define EQB_FLAG_NO_TMA 64u       /* staged kernel: cp.async row chunks instead of TMA     */
 #define EQB_FLAG_NO_LEAN 1024u    /* experiments: generic staged kernel where the lean     \
                                      variant would run                                     */
+#define EQB_FLAG_NO_LEAN2 4096u   /* experiments: the round-1 lean kernel where the strip-node \
+                                     kernel (remap_lean2.cuh) would run                    */
 #define EQB_FLAG_CHANNELS_LAST 2048u /* src and dst are channels-last (NHWC): channel stride  \
                                        1, pixel stride = channels; strides_h in elements.     \
                                        Served for uint8 RGB / RGBX bilinear equi2equi and     \
