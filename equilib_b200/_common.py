@@ -169,6 +169,8 @@ def flags_of(dtype: torch.dtype, opt: "Options") -> int:
         flags |= _lib.FLAG_NO_LEAN
     if os.environ.get("EQUILIB_B200_NO_LEAN2") == "1":
         flags |= _lib.FLAG_NO_LEAN2
+    if os.environ.get("EQUILIB_B200_FORCE_LEAN2") == "1":
+        flags |= _lib.FLAG_FORCE_LEAN2
     return flags
 
 

@@ -346,7 +346,11 @@ static bool can_lean2(const eqb_remap_desc* d) {
   if (reinterpret_cast<uintptr_t>(d->src) % 16) return false;
   if (d->src_stride_b % per16 || d->src_stride_c % per16 || d->src_stride_h % per16) return false;
   if (d->src_w > 65536 || d->src_h > 65536 || d->src_w < 16 || d->src_h < 16) return false;
-  if (elt == 1) {  // uint8 results leave as pixel pairs
+  if (elt == 1) {
+    // measured (gpurun_out/check_lean2.log): 2-byte stores of pixel pairs make the strip-node
+    // kernel slower than the round-1 lean kernel on uint8 (1.71 vs 1.40 ms on the bench
+    // rotations); uint8 stays there unless asked for (EQB_FLAG_FORCE_LEAN2, experiments)
+    if (!(d->flags & EQB_FLAG_FORCE_LEAN2)) return false;
     if (reinterpret_cast<uintptr_t>(d->dst) % 2) return false;
     if (d->dst_stride_b % 2 || d->dst_stride_c % 2 || d->dst_stride_h % 2) return false;
   }
@@ -381,7 +385,7 @@ static void setup_tma_l2(const eqb_remap_desc* d, Params& p) {
   for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
   for (int m = 0; m < kL2Boxes; ++m) {
     const int bw = l2_box_w(elt, m), bh = l2_box_h(elt, d->channels, m);
-    if (bw > 256 || bh < 12) continue;
+    if (bw > 256 || bh < kL2MinBoxH) continue;
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)d->channels, 1};
     if (enc(&p.tmaps[m], dt, 4, const_cast<void*>(d->src), dims, strides, box, ones,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -1,10 +1,11 @@
 // remap_lean2_kernel: the round-2 headline kernel -- bilinear, TMA-staged, planar 1 / 3 / 4
-// channels, equi2equi / equi2pers / equi2cube -- built around three measurements of the
-// round-1 lean kernel (profiles/r01_ncu_remap_bf16_v6_lean_final.txt: 147 instructions per
-// pixel, L1 data pipe 82 %, 2.3 wavefronts per 2-byte tap load):
+// channels, equi2equi / equi2pers / equi2cube.  Designed from ncu captures of its predecessors
+// (profiles/r01_ncu_remap_bf16_v6_lean_final.txt: 147 instructions per pixel, L1 data pipe
+// 82 %, 2.3 wavefronts per 2-byte tap; profiles/r02_ncu_lean2_v1.txt: 5.3x the source bytes
+// fetched as TMA boxes, a fifth of all issued instructions spinning on the box barrier):
 //
 //  1. COORDINATES FROM A STRIP-WIDE NODE GRID.  A CTA walks a strip of up to 8 tiles
-//     (64 x 8 pixels each) along x.  Before the first tile all 128 threads evaluate the
+//     (32 x 16 pixels each) along x.  Before the first tile all 128 threads evaluate the
 //     exact coordinate chain at the strip's NODES -- every 8th column of every row, plus one
 //     column on either side -- into shared memory (fully occupied warps: 1/8 node per pixel
 //     instead of the 1/4 of round 1, where every lane computed its own).  A pixel then gets
@@ -13,25 +14,27 @@
 //     their 8-pixel interval), as differences from the nearest node: 4 LDS.64 + 3 packed
 //     subtractions + 3 FFMA2 per pixel, no shuffles, no weight loads.
 //  2. PER-TILE HEADERS.  The same prologue reduces each tile's node hull to its TMA box
-//     (origin, shape) and to three flags -- smooth (4th and 2nd differences of the nodes
-//     small: the interpolation error is below 1e-3 px and no pixel leaves the node hull by
-//     more than 1/4 px, so no per-pixel "inside the box" test is needed), interior (no clamp,
-//     no wrap, no footprint shift can trigger) and straddling the seam.  The tile loop then
-//     runs without bounding-box reductions, votes, clamps or wraps on its common path.
-//  3. ONE BANK PER LANE.  A lane owns four pixels 16 apart (2-byte and 4-byte types) or two
-//     pairs (uint8), so the 16 lanes of a row read 16 ADJACENT source pixels per tap
-//     instruction: 32 (64) contiguous bytes instead of the 128 strided bytes of 4-pixel
-//     lanes, and box pitches are chosen so that the warp's second lane row lands in the
-//     other half of the banks (pitch * elt = 64 mod 128).
+//     (origin, shape) and to flags -- smooth (4th and 2nd differences of the nodes small: the
+//     interpolation error is below 1e-3 px and no pixel leaves the node hull by more than
+//     1/4 px, so no per-pixel "inside the box" test is needed), border (a clamp, the wrap or
+//     the footprint shift at the last column could trigger), seam.  Smooth interior tiles
+//     with a box take a straight-line fast path: no reductions, votes, clamps or wraps.
+//  3. SQUARER TILES, TWO BOX BUFFERS.  A 32 x 16 tile of a view rolled by 0.3 rad needs a
+//     48 x 30 box where the 64 x 8 tile of round 1 needed 96 x 40: less than half the L2 ->
+//     shared traffic per pixel.  The box of the NEXT tile is requested while the current one
+//     is blended (two buffers, full / empty mbarriers per buffer, no __syncthreads in the tile
+//     loop, waits back off with nanosleep instead of spinning on the issue slots).
+//  4. ALIGNED-WORD TAPS.  The 16 lanes of a row read 16 ADJACENT source pixels per tap
+//     instruction.  A 1- or 2-byte tap is fetched as the aligned 32-bit word that holds it
+//     (lanes sharing a word read the same address: a broadcast, one wavefront) and moved
+//     into place by one PRMT with a per-pixel selector -- the same two instructions as
+//     LDS.U16 + shift, without the extra wavefronts of sub-word accesses (measured: 1.7 per
+//     LDS.U16 when neighbouring lanes read the two halves of one word).
 //
-// Synchronisation: no __syncthreads in the tile loop.  The one box buffer is handed over with
-// two mbarriers: `full` (TMA completion) and `empty` (one arrival per warp when it is done
-// reading the tile); thread 0 waits for `empty` of the previous tile before it issues the
-// next box, every other thread runs ahead into the next tile's coordinate arithmetic.
-//
-// Tiles that are not smooth (source poles), ragged tiles and the EXACT variant evaluate the
-// exact chain on every pixel; tiles whose footprint fits no box (poles, seam) gather from
-// global memory -- same values on every path (tests: test_staged_and_direct_kernels_agree).
+// Tiles that are not smooth (source poles), border / seam / ragged tiles and the EXACT variant
+// evaluate the exact chain on every pixel; tiles whose footprint fits no box (poles, seam)
+// gather from global memory -- same values on every path
+// (tests: test_staged_and_direct_kernels_agree).
 #pragma once
 
 #include "remap_kernels.cuh"
@@ -39,40 +42,37 @@
 namespace eqb {
 
 constexpr int kL2Warps = 4;
-constexpr int kL2TileW = 64, kL2TileH = 8;
-constexpr int kL2Step = 8;                         // node spacing along x
-constexpr int kL2MaxIters = 8;                     // tiles per strip
-constexpr int kL2Cols = kL2MaxIters * 8 + 3;       // node columns -1 .. 8 * iters + 1
-constexpr int kL2Boxes = 13;
+constexpr int kL2TileW = 32, kL2TileH = 16;
+constexpr int kL2Step = 8;                          // node spacing along x
+constexpr int kL2MaxIters = 8;                      // tiles per strip
+constexpr int kL2Cols = kL2MaxIters * 4 + 3;        // node columns -1 .. 4 * iters + 1
+constexpr int kL2Boxes = 11;
+constexpr int kL2MinBoxH = kL2TileH + 5;            // an upright tile: 16 rows + 1 + margins
 static_assert(kL2Boxes <= kTmaSlots, "tensor-map slots");
 
-// Box buffer per CTA.  1- and 2-byte pixels: 22.5 KB, so that buffer + node grid + headers stay
-// under the 27.5 KB that let eight CTAs share an SM.
-EQB_HD constexpr int l2_smem_bytes(int elt) { return elt == 4 ? 32 * 1024 : 23040; }
+// One box buffer (a CTA holds two).
+EQB_HD constexpr int l2_buf_bytes(int elt) { return elt == 4 ? 16 * 1024 : 12 * 1024; }
 
-// Box m: l2_box_w x l2_box_h source pixels x channels.  1- and 2-byte pixels: pitches of 96 /
-// 160 / 224 pixels put consecutive rows 64 (mod 128) bytes apart for 2-byte pixels and 32 / 96
-// for bytes; 4-byte pixels use 80 / 112 / 144 / 176 (64 mod 128).  Boxes 0-2 are small
-// (upright and mildly rolled views: less L2 -> shared traffic); the others spend the whole
-// budget in different aspect ratios (see box_w in remap_kernels.cuh for the reasoning).
+// Box m: l2_box_w x l2_box_h source pixels x channels.  Boxes 0-1 are small (upright and
+// mildly rolled views); the others spend the whole buffer in different aspect ratios: 48
+// wide for rolls, 64-96 for the longitude stretch 1 / cos(lat) at high source latitudes,
+// 40 / 32 for rolls beyond 45 degrees.  pick = the first that fits.
 EQB_HD constexpr int l2_box_w(int elt, int m) {
-  const int w2 = m <= 3 ? 96 : m == 4 ? 160 : m == 5 ? 224 : m == 6 ? 128 : m == 7 ? 72 :
-                 m == 8 ? 64 : m == 9 ? 56 : m == 10 ? 48 : m == 11 ? 256 : 192;
-  const int w4 = m <= 3 ? 80 : m == 4 ? 112 : m == 5 ? 144 : m == 6 ? 176 : m == 7 ? 48 :
-                 m == 8 ? 64 : m == 9 ? 96 : m == 10 ? 208 : m == 11 ? 240 : 128;
-  const int w = elt == 4 ? w4 : w2;
+  const int w = m <= 2 ? 48 : m == 3 ? 64 : m == 4 ? 56 : m == 5 ? 80 : m == 6 ? 72 :
+                m == 7 ? 88 : m == 8 ? 96 : m == 9 ? 40 : 32;
   const int per16 = 16 / elt;
   return (w + per16 - 1) / per16 * per16;
 }
 EQB_HD constexpr int l2_box_h(int elt, int nc, int m) {
-  const int budget = l2_smem_bytes(elt) / elt / nc;
+  const int budget = l2_buf_bytes(elt) / elt / nc;
   const int full = budget / l2_box_w(elt, m) < 128 ? budget / l2_box_w(elt, m) : 128;
-  const int small = m == 0 ? 16 : m == 1 ? 24 : 32;
-  return m < 3 && small < full ? small : full;
+  const int small = m == 0 ? 24 : 32;
+  return m < 2 && small < full ? small : full;
 }
 
 // Cubic Lagrange weights of the nodes at -8, 0, +8, +16 for the pixel at offset t (0..7)
-// from the second one; w[t][1] is not stored (the weights sum to 1: u = n1 + sum w_j (n_j - n1)).
+// from the second one; the weight of that node is not stored (the weights sum to 1:
+// u = n1 + sum w_j (n_j - n1)).
 struct L2Weights { float w[8][3]; };
 constexpr L2Weights make_l2_weights() {
   L2Weights r{};
@@ -90,6 +90,20 @@ enum : int { L2_SMOOTH = 1, L2_BORDER = 2, L2_STRADDLE = 4, L2_RAGGED = 8, L2_BA
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Wait that yields the issue slots: one probe, then probes 32 ns apart.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(32);
+  }
 }
 
 // Rays of the cube faces as coded in torch_utils/grid.py:137-171 (F R B L U D).
@@ -135,32 +149,67 @@ __device__ __forceinline__ void node_coords(const Params& p, const RowCtx<XF>& c
   }
 }
 
-// One tap of channel plane offset OFF (bytes, compile time) as fp32.
-template <typename T, int OFF> __device__ __forceinline__ float l2_tap(unsigned addr) {
+// ---- taps --------------------------------------------------------------------------------
+// Sampling state of one pixel on the fast path: the word addresses of its left and right taps
+// (row y0, channel 0) and the PRMT selectors that move the tap out of its word.
+struct L2Px {
+  unsigned a0, a1;  // shared-memory byte addresses
+  unsigned s0, s1;  // PRMT selectors (fp16 / fp32: unused)
+};
+
+template <typename T>
+__device__ __forceinline__ void l2_px_setup(unsigned a, L2Px& q) {
+  if (sizeof(T) == 2 && !cuda::std::is_same<T, __half>::value) {
+    // bf16 -> fp32 is "the 16 bits in the upper half": selector 0x1044 lifts the low half of
+    // the word ([0, 0, b0, b1]), 0x3244 keeps the high half ([0, 0, b2, b3])
+    q.a0 = a & ~3u;
+    q.a1 = (a + 2u) & ~3u;
+    q.s0 = (a & 2u) ? 0x3244u : 0x1044u;
+    q.s1 = q.s0 ^ 0x2200u;
+  } else if (sizeof(T) == 1) {
+    // byte k of the word into byte 0 of 0x4B0000kk = 2^23 + k
+    q.a0 = a & ~3u;
+    q.a1 = (a + 1u) & ~3u;
+    q.s0 = 0x7540u | (a & 3u);
+    q.s1 = 0x7540u | ((a + 1u) & 3u);
+  } else {
+    q.a0 = a;
+    q.a1 = a + (unsigned)sizeof(T);
+    q.s0 = q.s1 = 0u;
+  }
+}
+
+// The tap at compile-time byte offset OFF (row / channel) from word address `addr`.
+template <typename T, int OFF>
+__device__ __forceinline__ float l2_tap(unsigned addr, unsigned sel) {
   if (sizeof(T) == 4) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
     return v;
   }
-  if (sizeof(T) == 1) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    // 2^23 + b, minus 2^23: full-rate pipes instead of the conversion unit
-    return __fsub_rn(__uint_as_float(v | 0x4B000000u), 8388608.0f);
+  if (cuda::std::is_same<T, __half>::value) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(OFF));
+    return __half2float(__ushort_as_half(v));
   }
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(OFF));
-  if (!cuda::std::is_same<T, __half>::value) return __uint_as_float((unsigned)v << 16);  // bf16
-  return __half2float(__ushort_as_half(v));
+  unsigned w;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w) : "r"(addr), "n"(OFF));
+  if (sizeof(T) == 1)
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 8388608.0f);
+  return __uint_as_float(__byte_perm(w, 0u, sel));
 }
 
-// Store of a lane's results for one channel.  P = 1: four pixels 16 apart; P = 2 (uint8): two
-// pairs 32 apart.  `d` points at the lane's first pixel of this channel.
+// Store of a lane's four results of one channel: d0 / d1 point at its pixels of the upper /
+// lower of its two rows.  2- and 4-byte types: pixels d[0], d[16]; uint8: the pair d[0..1].
 template <typename T>
-__device__ __forceinline__ void l2_store(T* d, const float (&o)[4], unsigned flags) {
+__device__ __forceinline__ void l2_store(T* d0, T* d1, const float (&o)[4], bool row1) {
   if constexpr (sizeof(T) == 4) {
-#pragma unroll
-    for (int g = 0; g < 4; ++g) __stcs(reinterpret_cast<float*>(d) + 16 * g, o[g]);
+    __stcs(reinterpret_cast<float*>(d0), o[0]);
+    __stcs(reinterpret_cast<float*>(d0) + 16, o[1]);
+    if (row1) {
+      __stcs(reinterpret_cast<float*>(d1), o[2]);
+      __stcs(reinterpret_cast<float*>(d1) + 16, o[3]);
+    }
   } else if constexpr (sizeof(T) == 2) {
     unsigned lo, hi;
     if constexpr (cuda::std::is_same<T, __half>::value) {
@@ -173,49 +222,53 @@ __device__ __forceinline__ void l2_store(T* d, const float (&o)[4], unsigned fla
       lo = *reinterpret_cast<const unsigned*>(&a);
       hi = *reinterpret_cast<const unsigned*>(&b);
     }
-    unsigned short* q = reinterpret_cast<unsigned short*>(d);
-    __stcs(q, (unsigned short)lo);
-    __stcs(q + 16, (unsigned short)(lo >> 16));
-    __stcs(q + 32, (unsigned short)hi);
-    __stcs(q + 48, (unsigned short)(hi >> 16));
+    unsigned short* q0 = reinterpret_cast<unsigned short*>(d0);
+    unsigned short* q1 = reinterpret_cast<unsigned short*>(d1);
+    __stcs(q0, (unsigned short)lo);
+    __stcs(q0 + 16, (unsigned short)(lo >> 16));
+    if (row1) {
+      __stcs(q1, (unsigned short)hi);
+      __stcs(q1 + 16, (unsigned short)(hi >> 16));
+    }
   } else {
     // bilinear code values are convex combinations: floor == the reference's truncation
     const unsigned t0 = u8_floor_bits(o[0]), t1 = u8_floor_bits(o[1]);
     const unsigned t2 = u8_floor_bits(o[2]), t3 = u8_floor_bits(o[3]);
-    unsigned short* q = reinterpret_cast<unsigned short*>(d);
-    __stcs(q, (unsigned short)__byte_perm(t0, t1, 0x0040u));
-    __stcs(q + 16, (unsigned short)__byte_perm(t2, t3, 0x0040u));
+    __stcs(reinterpret_cast<unsigned short*>(d0), (unsigned short)__byte_perm(t0, t1, 0x0040u));
+    if (row1)
+      __stcs(reinterpret_cast<unsigned short*>(d1), (unsigned short)__byte_perm(t2, t3, 0x0040u));
   }
 }
 
 // Blend + store of one channel from box M: pixel pairs (0, 1) and (2, 3) share FFMA2s.
 template <typename T, int M, int NC, int CI>
-__device__ __forceinline__ void l2_blend_channel(const unsigned (&a)[4],
+__device__ __forceinline__ void l2_blend_channel(const L2Px (&q)[4],
                                                  const unsigned long long (&w_nw)[2],
                                                  const unsigned long long (&w_ne)[2],
                                                  const unsigned long long (&w_sw)[2],
-                                                 const unsigned long long (&w_se)[2], T* dst,
-                                                 long long dsc, unsigned flags) {
+                                                 const unsigned long long (&w_se)[2], T* d0,
+                                                 T* d1, long long dsc, bool row1) {
   constexpr int ELT = (int)sizeof(T);
   constexpr int ROW = l2_box_w(ELT, M) * ELT;
   constexpr int CH = CI * ROW * l2_box_h(ELT, NC, M);
   float o[4];
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const unsigned a0 = a[2 * k], a1 = a[2 * k + 1];
-    unsigned long long acc = mul2(pk2(l2_tap<T, CH>(a0), l2_tap<T, CH>(a1)), w_nw[k]);
-    acc = fma2(pk2(l2_tap<T, CH + ELT>(a0), l2_tap<T, CH + ELT>(a1)), w_ne[k], acc);
-    acc = fma2(pk2(l2_tap<T, CH + ROW>(a0), l2_tap<T, CH + ROW>(a1)), w_sw[k], acc);
-    acc = fma2(pk2(l2_tap<T, CH + ROW + ELT>(a0), l2_tap<T, CH + ROW + ELT>(a1)), w_se[k], acc);
+    const L2Px &x = q[2 * k], &y = q[2 * k + 1];
+    unsigned long long acc =
+        mul2(pk2(l2_tap<T, CH>(x.a0, x.s0), l2_tap<T, CH>(y.a0, y.s0)), w_nw[k]);
+    acc = fma2(pk2(l2_tap<T, CH>(x.a1, x.s1), l2_tap<T, CH>(y.a1, y.s1)), w_ne[k], acc);
+    acc = fma2(pk2(l2_tap<T, CH + ROW>(x.a0, x.s0), l2_tap<T, CH + ROW>(y.a0, y.s0)), w_sw[k], acc);
+    acc = fma2(pk2(l2_tap<T, CH + ROW>(x.a1, x.s1), l2_tap<T, CH + ROW>(y.a1, y.s1)), w_se[k], acc);
     unpk2(acc, o[2 * k], o[2 * k + 1]);
   }
-  l2_store<T>(dst + CI * dsc, o, flags);
+  l2_store<T>(d0 + CI * dsc, d1 + CI * dsc, o, row1);
 }
 
 template <typename T, int M, int NC>
-__device__ __forceinline__ void l2_blend(const unsigned (&a)[4], const float (&fx)[4],
-                                         const float (&fy)[4], T* dst, long long dsc,
-                                         unsigned flags) {
+__device__ __forceinline__ void l2_blend(const L2Px (&q)[4], const float (&fx)[4],
+                                         const float (&fy)[4], T* d0, T* d1, long long dsc,
+                                         bool row1) {
   const unsigned long long one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
   unsigned long long w_nw[2], w_ne[2], w_sw[2], w_se[2];
 #pragma unroll
@@ -227,23 +280,23 @@ __device__ __forceinline__ void l2_blend(const unsigned (&a)[4], const float (&f
     w_sw[k] = mul2(ax, by);
     w_se[k] = mul2(bx, by);
   }
-  l2_blend_channel<T, M, NC, 0>(a, w_nw, w_ne, w_sw, w_se, dst, dsc, flags);
-  if constexpr (NC > 1) l2_blend_channel<T, M, NC, 1>(a, w_nw, w_ne, w_sw, w_se, dst, dsc, flags);
-  if constexpr (NC > 2) l2_blend_channel<T, M, NC, 2>(a, w_nw, w_ne, w_sw, w_se, dst, dsc, flags);
-  if constexpr (NC > 3) l2_blend_channel<T, M, NC, 3>(a, w_nw, w_ne, w_sw, w_se, dst, dsc, flags);
+  l2_blend_channel<T, M, NC, 0>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+  if constexpr (NC > 1) l2_blend_channel<T, M, NC, 1>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+  if constexpr (NC > 2) l2_blend_channel<T, M, NC, 2>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+  if constexpr (NC > 3) l2_blend_channel<T, M, NC, 3>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
 }
 
 template <int XF, typename T, int NC, bool EXACT>
-__global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8)
+__global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7)
     remap_lean2_kernel(const __grid_constant__ Params p) {
   constexpr int ELT = (int)sizeof(T);
   constexpr int PER16 = 16 / ELT;
-  constexpr int P = ELT == 1 ? 2 : 1;  // adjacent pixels per group: a group is >= 2 bytes
-  constexpr int G = 4 / P;             // groups per lane, 16 * P pixels apart
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int P = ELT == 1 ? 2 : 1;  // adjacent pixels per lane and row: a group is >= 2 bytes
+  constexpr int BUF = l2_buf_bytes(ELT);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // two box buffers
   __shared__ __align__(16) float2 nodes[kL2TileH][kL2Cols + 1];  // (ui, uj)
   __shared__ __align__(16) int4 headers[kL2MaxIters];
-  __shared__ __align__(8) unsigned long long full_bar, empty_bar;
+  __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z;
@@ -255,8 +308,10 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
   const bool background = XF == EQB_EQUI2CUBE && cell >= 6;
 
   if (tid == 0) {
-    mbar_init(&full_bar, 1);
-    mbar_init(&empty_bar, kL2Warps);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], kL2Warps);
+    mbar_init(&empty_bar[1], kL2Warps);
   }
 
   // ---- prologue 1: the exact chain at the strip's nodes -------------------------------
@@ -265,8 +320,8 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
     const int y = min(tile_y0 + row, p.dh - 1);
     RowCtx<XF> rc;
     row_setup<XF>(p, b, y, rc);
-    const int ncols = ntiles * 8 + 3;
-    for (int col = tid >> 3; col < ncols; col += kL2Warps * 32 / kL2TileH) {
+    const int ncols = ntiles * 4 + 3;
+    for (int col = tid >> 4; col < ncols; col += kL2Warps * 32 / kL2TileH) {
       float uj, ui;
       node_coords<XF>(p, rc, strip_x0 + kL2Step * (col - 1), y, cell, uj, ui);
       nodes[row][col] = make_float2(ui, uj);
@@ -285,23 +340,20 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
         if (lane == 0) headers[k] = make_int4(0, 0, -1, flags | L2_BACKGROUND);
         continue;
       }
-      // window of five nodes centred on tile-local node column c = 1, 3, 5, 7 of row r
-      const int r = lane & 7, c = 1 + 2 * (lane >> 3);
-      const float2* np = &nodes[r][k * 8 + c - 1];  // (array index = node column + 1)
+      // window of five nodes centred on tile-local node column c = 1 or 3 of row r: the
+      // tile's own columns are 0..4, the windows also see -1 and 5 (interpolation stencils)
+      const int r = lane & 15, c = 1 + 2 * (lane >> 4);
+      const float2* np = &nodes[r][k * 4 + c - 1];  // (array index = node column + 1)
       float2 n[5];
 #pragma unroll
       for (int i = 0; i < 5; ++i) n[i] = np[i];
-      // hull of the tile's own node columns 0..8 (the windows also see columns -1 and 9,
-      // which only matter for the seam: `alo / ahi` span all five)
-      float ulo = n[1].x, uhi = n[1].x, vlo = n[1].y, vhi = n[1].y;
-      float alo = fminf(n[0].x, n[4].x), ahi = fmaxf(n[0].x, n[4].x);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        if ((i == 0 && c == 1) || (i == 4 && c == 7) || i == 1) continue;
-        ulo = fminf(ulo, n[i].x); uhi = fmaxf(uhi, n[i].x);
-        vlo = fminf(vlo, n[i].y); vhi = fmaxf(vhi, n[i].y);
-      }
-      alo = fminf(alo, ulo); ahi = fmaxf(ahi, uhi);
+      float ulo = fminf(fminf(n[1].x, n[2].x), n[3].x), uhi = fmaxf(fmaxf(n[1].x, n[2].x), n[3].x);
+      float vlo = fminf(fminf(n[1].y, n[2].y), n[3].y), vhi = fmaxf(fmaxf(n[1].y, n[2].y), n[3].y);
+      const float2 e = c == 1 ? n[4] : n[0];  // the end node that is a column of the tile
+      ulo = fminf(ulo, e.x); uhi = fmaxf(uhi, e.x);
+      vlo = fminf(vlo, e.y); vhi = fmaxf(vhi, e.y);
+      const float2 f = c == 1 ? n[0] : n[4];  // the one outside
+      const float alo = fminf(ulo, f.x), ahi = fmaxf(uhi, f.x);
       // (coordinates are >= 0: their bit patterns order like integers)
       const float umin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(ulo)));
       const float umax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(uhi)));
@@ -310,33 +362,24 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
       const float amin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(alo)));
       const float amax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(ahi)));
       // the tile's own footprint wraps around the seam (no single box holds it) / some node of
-      // its interpolation stencils lies across the seam (differences must be unwrapped)
+      // its interpolation stencils lies across the seam (such tiles take the exact chain)
       const bool box_straddle = umax - umin >= 0.5f * p.swf;
       const bool straddle = amax - amin >= 0.5f * p.swf;
-      // smoothness: 4th difference (the cubic's error is ~0.023 of it) and 2nd differences
-      // (a pixel leaves the hull of its neighbouring nodes by at most 1/8 of them)
-      float d[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = i < 2 ? i : i + 1;
-        d[i][0] = n[j].x - n[2].x;
-        d[i][1] = n[j].y - n[2].y;
-        if (straddle) {
-          if (d[i][0] > 0.5f * p.swf) d[i][0] -= p.swf;
-          if (d[i][0] < -0.5f * p.swf) d[i][0] += p.swf;
-        }
-      }
-      bool ok = true;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const float d4 = (d[0][q] + d[3][q]) - 4.0f * (d[1][q] + d[2][q]);
-        const float d2a = d[1][q] + d[2][q];
-        const float d2b = d[0][q] - 2.0f * d[1][q];
-        const float d2c = d[3][q] - 2.0f * d[2][q];
-        ok = ok && fabsf(d4) < 0.03f && fabsf(d2a) < 2.0f && fabsf(d2b) < 2.0f && fabsf(d2c) < 2.0f;
+      // smoothness: 4th difference (the cubic's error is ~0.023 of it) and 2nd difference (a
+      // pixel leaves the hull of its neighbouring nodes by at most 1/8 of it), from differences
+      // against the centre node (no cancellation at coordinates of order 4096)
+      bool ok = !straddle;
+      {
+        const float ax = n[0].x - n[2].x, bx = n[1].x - n[2].x, cx = n[3].x - n[2].x,
+                    dx = n[4].x - n[2].x;
+        const float ay = n[0].y - n[2].y, by = n[1].y - n[2].y, cy = n[3].y - n[2].y,
+                    dy = n[4].y - n[2].y;
+        const float d4x = (ax + dx) - 4.0f * (bx + cx), d4y = (ay + dy) - 4.0f * (by + cy);
+        const float d2x = bx + cx, d2y = by + cy;
+        ok = ok && fmaxf(fabsf(d4x), fabsf(d4y)) < 0.03f && fmaxf(fabsf(d2x), fabsf(d2y)) < 1.5f;
       }
       if (__all_sync(0xffffffffu, ok)) flags |= L2_SMOOTH;
-      if (straddle) flags |= L2_STRADDLE | L2_BORDER;
+      if (straddle) flags |= L2_STRADDLE;
       if (umin < 1.0f || umax > p.swm1f - 2.0f || vmin < 1.0f || vmax > p.shm1f - 2.0f)
         flags |= L2_BORDER;
       // box: top-left taps of the hull (with the footprint shift at the last column / row),
@@ -357,14 +400,17 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
   __syncthreads();
 
   // ---- tile loop ---------------------------------------------------------------------------
+  // lane (lx, ly) of warp w owns, in rows 4w + ly and 4w + ly + 2, the pixels lx and lx + 16
+  // (uint8: the pair 2 lx, 2 lx + 1).  Pixel j: row j >> 1, column slot j & 1.
   const int lx = lane & 15, ly = lane >> 4;
-  const int row = warp * 2 + ly;
-  const int yq = tile_y0 + row;
-  const int y = min(yq, p.dh - 1);
+  const int row0 = warp * 4 + ly;
+  const int y0q = tile_y0 + row0;
+  const bool row0_ok = y0q < p.dh, row1_ok = y0q + 2 < p.dh;
   const unsigned tile_s = smem_u32(smem_raw);
   const T* const src_b = static_cast<const T*>(p.src) + (long long)b * p.ssb;
-  T* const dst_row = static_cast<T*>(p.dst) + (long long)b * p.dsb + (long long)y * p.dsh;
+  T* const dst_b = static_cast<T*>(p.dst) + (long long)b * p.dsb;
   const int ssh = (int)p.ssh;
+  auto xloc = [&](int j) { return P == 1 ? lx + 16 * (j & 1) : 2 * lx + (j & 1); };
   // interpolation weights of this lane's pixels (offset t inside their 8-pixel interval)
   unsigned long long wt[P][3];
 #pragma unroll
@@ -373,149 +419,119 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
 #pragma unroll
     for (int j = 0; j < 3; ++j) wt[q][j] = pk2(g_l2_weights.w[t][j], g_l2_weights.w[t][j]);
   }
-  RowCtx<XF> rc;
-  if (EXACT) row_setup<XF>(p, b, y, rc);
-  // boxed tiles so far: phase of both mbarriers.  Only boxed tiles touch them -- a warp that
-  // arrived on `empty` for tiles it ran through without a box could complete a phase while a
-  // slower warp still reads the buffer.
+
+  // The box of boxed tile n lives in buffer n & 1; phase parity of its barriers (n >> 1) & 1.
+  // Thread 0 requests the box of the NEXT boxed tile while the current one is blended.
+  auto issue = [&](int k, unsigned n) {  // thread 0 only
+    const int4 h = headers[k];
+    const unsigned buf = n & 1u;
+    if (n >= 2) mbar_wait_backoff(&empty_bar[buf], ((n >> 1) - 1u) & 1u);
+    mbar_expect_tx(&full_bar[buf], (unsigned)(p.tma_bw[h.z] * p.tma_bh[h.z] * NC * ELT));
+    tma_load_box(smem_raw + buf * BUF, &p.tmaps[h.z], &full_bar[buf], h.x, h.y, 0,
+                 p.tma_batched ? b : 0);
+  };
+  auto next_boxed = [&](int k) {
+    for (++k; k < ntiles; ++k)
+      if (headers[k].z >= 0) return k;
+    return -1;
+  };
   unsigned nbox = 0;
+  if (tid == 0) {
+    const int k0 = next_boxed(-1);
+    if (k0 >= 0) issue(k0, 0);
+  }
 
   for (int k = 0; k < ntiles; ++k) {
     const int4 hdr = headers[k];
     const int gx0 = hdr.x, gy0 = hdr.y, m = hdr.z, flags = hdr.w;
     const int tile_x0 = strip_x0 + k * kL2TileW;
     const bool boxed = m >= 0;
-    if (tid == 0 && boxed) {
-      // the buffer is free once every warp has arrived for the previous boxed tile
-      if (nbox > 0) mbar_wait(&empty_bar, (nbox - 1) & 1u);
-      const int bw = p.tma_bw[m], bh = p.tma_bh[m];
-      mbar_expect_tx(&full_bar, (unsigned)(bw * bh * NC * ELT));
-      tma_load_box(smem_raw, &p.tmaps[m], &full_bar, gx0, gy0, 0, p.tma_batched ? b : 0);
-    }
-    __syncwarp();
-
-    // this lane's pixels: tile-local x of pixel j
-    auto xloc = [&](int j) { return (j / P) * 16 * P + lx * P + (j % P); };
-    T* dst = dst_row + tile_x0 + lx * P;
-    if (XF == EQB_EQUI2CUBE) dst = dst_row + p.cell_off[cell] + (tile_x0 - cell * p.w_face) + lx * P;
+    T* d0 = dst_b + (long long)min(y0q, p.dh - 1) * p.dsh + tile_x0 + lx * P;
+    if (XF == EQB_EQUI2CUBE)
+      d0 = dst_b + (long long)min(y0q, p.dh - 1) * p.dsh + p.cell_off[cell] +
+           (tile_x0 - cell * p.w_face) + lx * P;
+    T* d1 = d0 + 2 * p.dsh;
 
     if (flags & L2_BACKGROUND) {  // dice background cell
-      if (yq < p.dh) {
+      if (row0_ok) {
         const float z[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < NC; ++c) l2_store<T>(dst + c * p.dsc, z, 0u);
+        for (int c = 0; c < NC; ++c) l2_store<T>(d0 + c * p.dsc, d1 + c * p.dsc, z, row1_ok);
       }
       continue;
     }
 
-    // ---- coordinates ------------------------------------------------------------------------
-    float ixa[4], iya[4];
-    const bool interp = !EXACT && (flags & (L2_SMOOTH | L2_RAGGED)) == L2_SMOOTH;
-    if (interp) {
-      const unsigned long long mone = pk2(-1.0f, -1.0f);
+    const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED)) == L2_SMOOTH
+                                      : (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE |
+                                                  L2_RAGGED)) == L2_SMOOTH);
+    if (fast) {
+      // ======== fast path: smooth tile with a box ==========================================
+      float ixa[4], iya[4];
+      if constexpr (!EXACT) {
+        const unsigned long long mone = pk2(-1.0f, -1.0f);
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const unsigned long long* np = reinterpret_cast<const unsigned long long*>(
-            &nodes[row][k * 8 + ((g * 16 * P + lx * P) >> 3)]);
-        const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
-        unsigned long long d0 = fma2(n1, mone, n0), d2 = fma2(n1, mone, n2),
-                           d3 = fma2(n1, mone, n3);
-        if (flags & L2_STRADDLE) {  // unwrap the longitude across the seam
-          auto unwrap = [&](unsigned long long& d) {
-            float di, dj;
-            unpk2(d, di, dj);
-            if (di > 0.5f * p.swf) di -= p.swf;
-            if (di < -0.5f * p.swf) di += p.swf;
-            d = pk2(di, dj);
-          };
-          unwrap(d0); unwrap(d2); unwrap(d3);
+        for (int g = 0; g < 4 / P; ++g) {
+          // P == 1: pixel g; P == 2: the pair (2g, 2g + 1) shares its stencil
+          const int r = row0 + 2 * ((g * P) >> 1);
+          const int iv = P == 1 ? (lx >> 3) + 2 * (g & 1) : (lx >> 2);
+          const unsigned long long* np =
+              reinterpret_cast<const unsigned long long*>(&nodes[r][k * 4 + iv]);
+          const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+          const unsigned long long d0n = fma2(n1, mone, n0), d2n = fma2(n1, mone, n2),
+                                   d3n = fma2(n1, mone, n3);
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const unsigned long long u =
+                fma2(wt[q][2], d3n, fma2(wt[q][1], d2n, fma2(wt[q][0], d0n, n1)));
+            unpk2(u, ixa[g * P + q], iya[g * P + q]);
+          }
         }
+      } else {
+        RowCtx<XF> rc;
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-          const unsigned long long u =
-              fma2(wt[q][2], d3, fma2(wt[q][1], d2, fma2(wt[q][0], d0, n1)));
-          unpk2(u, ixa[g * P + q], iya[g * P + q]);
-        }
-      }
-      if (flags & L2_BORDER) {
+        for (int gy = 0; gy < 2; ++gy) {
+          const int y = min(y0q + 2 * gy, p.dh - 1);
+          row_setup<XF>(p, b, y, rc);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ixa[j] < 0.0f) ixa[j] += p.swf;
-          if (ixa[j] >= p.swf) ixa[j] -= p.swf;
-          // the normalise / un-normalise round trip is clamp(u, 0, size-1) up to rounding
-          ixa[j] = fminf(ixa[j], p.swm1f);
-          iya[j] = fminf(fmaxf(iya[j], 0.0f), p.shm1f);
-        }
-      }
-    } else {
-      if (!EXACT) row_setup<XF>(p, b, y, rc);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int x = min(tile_x0 + xloc(j), p.dw - 1);
-        float uj, ui;
-        coords<XF, false>(p, rc, b, x, y, cell, min(x - cell * p.w_face, p.w_face - 1), uj, ui);
-        ixa[j] = to_index(ui, p.inv_wm1, p.swm1f);
-        iya[j] = to_index(uj, p.inv_hm1, p.shm1f);
-      }
-    }
-
-    // ---- per-pixel sampling state --------------------------------------------------------------
-    // (interior smooth tiles: no footprint shift can trigger, every tap is inside the box)
-    const bool plain = interp && !(flags & L2_BORDER);
-    unsigned a[4];
-    float fx[4], fy[4];
-    bool inside = true;
-    {
-      float xf[4], yf[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        xf[j] = floorf(ixa[j]);
-        yf[j] = floorf(iya[j]);
-      }
-      if (!plain) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
-          xf[j] = fminf(xf[j], p.swm1f - 1.0f);
-          yf[j] = fminf(yf[j], p.shm1f - 1.0f);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        fx[j] = __fsub_rn(ixa[j], xf[j]);
-        fy[j] = __fsub_rn(iya[j], yf[j]);
-      }
-      if (boxed) {
-        const int pitch = p.tma_bw[m];
-        const float pitchf = (float)pitch;
-        // byte address = ((yf - gy0) * pitch + (xf - gx0)) * ELT + tile_s; yf * pitch + xf is an
-        // exact integer below 2^24
-        const int base = (int)tile_s - (gy0 * pitch + gx0) * ELT;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          a[j] = (unsigned)((int)fmaf(yf[j], pitchf, xf[j]) * ELT + base);
-        if (!(flags & L2_SMOOTH) || (flags & L2_RAGGED)) {
-          const float gx0f = (float)gx0, gy0f = (float)gy0;
-          const float xlim = (float)(pitch - 2), ylim = (float)(p.tma_bh[m] - 2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float xr = xf[j] - gx0f, yr = yf[j] - gy0f;
-            inside = inside && xr >= 0.0f && xr <= xlim && yr >= 0.0f && yr <= ylim;
+          for (int s = 0; s < 2; ++s) {
+            const int j = 2 * gy + s, x = tile_x0 + xloc(j);
+            float uj, ui;
+            coords<XF, false>(p, rc, b, x, y, cell, x - cell * p.w_face, uj, ui);
+            ixa[j] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[j] = to_index(uj, p.inv_hm1, p.shm1f);
           }
         }
       }
-      if (!boxed || !inside) {
+      L2Px px[4];
+      float fx[4], fy[4];
+      {
+        const int pitch = p.tma_bw[m];
+        const float pitchf = (float)pitch;
+        // byte address = ((yf - gy0) * pitch + (xf - gx0)) * ELT + buffer; yf * pitch + xf is
+        // an exact integer below 2^24
+        const int base = (int)(tile_s + (nbox & 1u) * BUF) - (gy0 * pitch + gx0) * ELT;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = (unsigned)((int)yf[j] * ssh + (int)xf[j]);
+        for (int j = 0; j < 4; ++j) {
+          float xf = floorf(ixa[j]), yf = floorf(iya[j]);
+          if (EXACT) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
+            xf = fminf(xf, p.swm1f - 1.0f);
+            yf = fminf(yf, p.shm1f - 1.0f);
+          }
+          fx[j] = __fsub_rn(ixa[j], xf);
+          fy[j] = __fsub_rn(iya[j], yf);
+          l2_px_setup<T>((unsigned)((int)fmaf(yf, pitchf, xf) * ELT + base), px[j]);
+        }
       }
-    }
-    if (boxed) mbar_wait(&full_bar, nbox & 1u);
-
-    // ---- blend and store ----------------------------------------------------------------------
-    const bool full_tile = !(flags & L2_RAGGED);
-    if (yq < p.dh) {
-      if (boxed && inside && full_tile) {
+      // request the next box, then wait for this one
+      if (tid == 0) {
+        const int k2 = next_boxed(k);
+        if (k2 >= 0) issue(k2, nbox + 1);
+      }
+      __syncwarp();
+      mbar_wait_backoff(&full_bar[nbox & 1u], (nbox >> 1) & 1u);
+      if (row0_ok) {
         auto blend_m = [&](auto mc) {
           constexpr int M = decltype(mc)::value;
-          l2_blend<T, M, NC>(a, fx, fy, dst, p.dsc, p.flags);
+          l2_blend<T, M, NC>(px, fx, fy, d0, d1, p.dsc, row1_ok);
         };
         switch (m) {
           case 0: blend_m(cuda::std::integral_constant<int, 0>{}); break;
@@ -528,54 +544,75 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 6 : 8
           case 7: blend_m(cuda::std::integral_constant<int, 7>{}); break;
           case 8: blend_m(cuda::std::integral_constant<int, 8>{}); break;
           case 9: blend_m(cuda::std::integral_constant<int, 9>{}); break;
-          case 10: blend_m(cuda::std::integral_constant<int, 10>{}); break;
-          case 11: blend_m(cuda::std::integral_constant<int, 11>{}); break;
-          default: blend_m(cuda::std::integral_constant<int, 12>{}); break;
+          default: blend_m(cuda::std::integral_constant<int, 10>{}); break;
         }
-      } else {
-        // slow paths: taps from the box through generic loads (ragged tiles) or from global
-        // memory (no box, or a tap outside it); element stores
-        float w_nw[4], w_ne[4], w_sw[4], w_se[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float ax = __fsub_rn(1.0f, fx[j]), ay = __fsub_rn(1.0f, fy[j]);
-          w_nw[j] = __fmul_rn(ax, ay);
-          w_ne[j] = __fmul_rn(fx[j], ay);
-          w_sw[j] = __fmul_rn(ax, fy[j]);
-          w_se[j] = __fmul_rn(fx[j], fy[j]);
-        }
-        const bool from_box = boxed && inside;
-        const int pitch = boxed ? p.tma_bw[m] : 0;
-        const int plane = boxed ? pitch * p.tma_bh[m] : 0;
-        for (int c = 0; c < NC; ++c) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (tile_x0 + xloc(j) >= p.dw) continue;
-            float v;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[nbox & 1u]);
+      ++nbox;
+      continue;
+    }
+
+    // ======== general path: exact chain on every pixel; box, or global gathers ==============
+    if (boxed) {
+      if (tid == 0) {
+        const int k2 = next_boxed(k);
+        if (k2 >= 0) issue(k2, nbox + 1);
+      }
+      __syncwarp();
+      mbar_wait_backoff(&full_bar[nbox & 1u], (nbox >> 1) & 1u);
+    }
+    {
+      const int pitch = boxed ? p.tma_bw[m] : 0;
+      const int bh = boxed ? p.tma_bh[m] : 0;
+      const T* const box = reinterpret_cast<const T*>(smem_raw + (nbox & 1u) * BUF);
+      RowCtx<XF> rc;
+#pragma unroll 1
+      for (int gy = 0; gy < 2; ++gy) {
+        const int yq = y0q + 2 * gy;
+        if (yq >= p.dh) break;
+        row_setup<XF>(p, b, yq, rc);
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          const int j = 2 * gy + s, x = tile_x0 + xloc(j);
+          if (x >= p.dw) continue;
+          float uj, ui;
+          coords<XF, false>(p, rc, b, x, yq, cell, x - cell * p.w_face, uj, ui);
+          const float ix = to_index(ui, p.inv_wm1, p.swm1f), iy = to_index(uj, p.inv_hm1, p.shm1f);
+          const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
+          const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
+          const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
+          const float w_nw = __fmul_rn(ax, ay), w_ne = __fmul_rn(bx, ay);
+          const float w_sw = __fmul_rn(ax, by), w_se = __fmul_rn(bx, by);
+          const int xi = (int)xf, yi = (int)yf;
+          const int xr = xi - gx0, yr = yi - gy0;
+          const bool from_box = boxed && xr >= 0 && xr <= pitch - 2 && yr >= 0 && yr <= bh - 2;
+          T* d = (gy ? d1 : d0) + (xloc(j) - lx * P);
+          for (int c = 0; c < NC; ++c) {
+            float v_nw, v_ne, v_sw, v_se;
             if (from_box) {
-              const T* q0 = reinterpret_cast<const T*>(smem_raw) + (a[j] - tile_s) / ELT + c * plane;
-              v = blend4(lds_f(q0), lds_f(q0 + 1), lds_f(q0 + pitch), lds_f(q0 + pitch + 1),
-                         w_nw[j], w_ne[j], w_sw[j], w_se[j]);
+              const T* q0 = box + (c * bh + yr) * pitch + xr;
+              v_nw = lds_f(q0); v_ne = lds_f(q0 + 1);
+              v_sw = lds_f(q0 + pitch); v_se = lds_f(q0 + pitch + 1);
             } else {
-              const T* q0 = src_b + (long long)c * p.ssc + (int)a[j];
-              float v_nw, v_ne, v_sw, v_se;
+              const T* q0 = src_b + (long long)c * p.ssc + (yi * ssh + xi);
               if constexpr (ELT == 4) {
                 v_nw = ld_f(q0); v_ne = ld_f(q0 + 1); v_sw = ld_f(q0 + ssh); v_se = ld_f(q0 + ssh + 1);
               } else {
                 ldg_pair<T>(q0, v_nw, v_ne);
                 ldg_pair<T>(q0 + ssh, v_sw, v_se);
               }
-              v = blend4(v_nw, v_ne, v_sw, v_se, w_nw[j], w_ne[j], w_sw[j], w_se[j]);
             }
-            const T o = OutCvt<T>::cvt(v, p.flags);
-            Pack<T, 1>::st(dst + c * p.dsc + (xloc(j) - lx * P), &o);
+            const T o = OutCvt<T>::cvt(blend4(v_nw, v_ne, v_sw, v_se, w_nw, w_ne, w_sw, w_se),
+                                       p.flags);
+            Pack<T, 1>::st(d + c * p.dsc, &o);
           }
         }
       }
     }
     if (boxed) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar);
+      if (lane == 0) mbar_arrive(&empty_bar[nbox & 1u]);
       ++nbox;
     }
   }

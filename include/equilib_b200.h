@@ -65,8 +65,11 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
                                    div / atan2 instead of their inlined fast paths   */
 #define EQB_FLAG_NO_STAGE 8u    /* never use the shared-memory staged kernel           */
 #define EQB_FLAG_EXACT_COORDS 16u /* 16/8-bit images: exact coordinate chain on every     \
-                                    pixel (default: every 4th pixel + cubic interpolation \
-                                    along x, error ~1e-6 px)                   */
+                                    pixel.  Default for these types: the chain on every    \
+                                    4th / 8th pixel of a row + cubic interpolation along  \
+                                    x -- measured <= 1.7e-3 px (mean 1.8e-4 px) from the   \
+                                    exact chain at 2048 x 4096, test bound 3e-3 px;        \
+                                    DESIGN.md 4.3                                          */
 #define EQB_FLAG_FAST_COORDS 32u  /* fp32 images: opt in to the interpolated coordinates  */
 #define EQB_FLAG_FORCE_STAGE 128u /* experiments: staged kernel wherever it is legal           */
 #define EQB_FLAG_NO_TMA 64u       /* staged kernel: cp.async row chunks instead of TMA     */
@@ -74,6 +77,7 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
                                      variant would run                                     */
 #define EQB_FLAG_NO_LEAN2 4096u   /* experiments: the round-1 lean kernel where the strip-node \
                                      kernel (remap_lean2.cuh) would run                    */
+#define EQB_FLAG_FORCE_LEAN2 8192u /* experiments: strip-node kernel for uint8 too          */
 #define EQB_FLAG_CHANNELS_LAST 2048u /* src and dst are channels-last (NHWC): channel stride  \
                                        1, pixel stride = channels; strides_h in elements.     \
                                        Served for uint8 RGB / RGBX bilinear equi2equi and     \
