@@ -18,15 +18,20 @@ SUPPORTED = (torch.uint8, torch.float16, torch.bfloat16, torch.float32)
 
 def check_backend(kwargs: dict) -> None:
     """The reference threads ``backend=`` ("native" | "pure") and ``cache=`` through
-    **kwargs (e.g. equilib/equi2pers/base.py:59-72,155).  Here the only backend is
-    the fused CUDA one; ``cache`` is accepted and ignored (tables are cached per
-    device in _prep)."""
+    **kwargs (e.g. equilib/equi2pers/base.py:59-72,155).  Here there is one sampler, the
+    fused CUDA one, and its parity target IS the reference's "native" backend
+    (F.grid_sample semantics, equilib/grid_sample/torch/native.py:80-88): ``backend="native"``
+    and ``"b200"`` both select it, so reference call sites that pass ``backend="native"``
+    explicitly keep working.  ``"pure"`` (the reference's index-gather sampler, which wraps
+    the seam and has a known tap bug, bilinear.py:47) is a different function and is not
+    emulated: it raises.  ``cache`` is accepted and ignored (tables are cached per device
+    in _prep)."""
     backend = kwargs.pop("backend", None)
     kwargs.pop("cache", None)
-    if backend not in (None, "b200"):
+    if backend not in (None, "b200", "native"):
         raise ValueError(
-            f"ERR: {backend} is not supported by equilib_b200 (only 'b200'); use the "
-            "reference package for the 'native' and 'pure' backends"
+            f"ERR: {backend} is not supported by equilib_b200 ('b200' / 'native' select the "
+            "fused CUDA sampler); use the reference package for the 'pure' backend"
         )
 
 

@@ -97,6 +97,7 @@ EXPORTS = {
     "eqb_minmax": (C.c_int32, [C.POINTER(Image), C.c_void_p, C.c_void_p]),
     "eqb_rotation_compose": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "eqb_launch_count": (C.c_int64, []),
+    "eqb_source_hash": (C.c_char_p, []),
 }
 
 _lock = threading.Lock()
@@ -136,6 +137,11 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = lib().eqb_last_error().decode("utf-8", "replace")
         raise EquilibB200Error(f"{what} failed (status {status}): {msg}")
+
+
+def source_hash() -> str:
+    """Source hash compiled into the loaded library (equilib_b200/build.py::source_hash)."""
+    return lib().eqb_source_hash().decode("ascii", "replace")
 
 
 def launch_count() -> int:

@@ -35,12 +35,28 @@ TABLE_CACHE_MAXSIZE = 16  # same bound as equilib/_cache.py:18
 MATS_CACHE_MAXSIZE = 64
 
 
+def _tensors(value):
+    if torch.is_tensor(value):
+        yield value
+    elif isinstance(value, (tuple, list)):
+        for v in value:
+            yield from _tensors(v)
+
+
 class _BoundedCache:
-    """Thread-safe FIFO-bounded dict (the reference's cached_grid policy)."""
+    """Thread-safe FIFO-bounded dict (the reference's cached_grid policy).
+
+    Entries are device tensors that launches on ANY stream read.  Two rules keep that safe
+    without per-use events: (1) an entry is published only after its upload has completed
+    (one host synchronisation of the uploading stream, once per entry); (2) an evicted
+    entry is parked in a second FIFO of the same size instead of being freed, so its memory
+    cannot be handed out again while a launch enqueued before the eviction may still read
+    it (a block would have to survive 2 x maxsize newer entries' worth of calls)."""
 
     def __init__(self, maxsize: int):
         self.maxsize = maxsize
         self._d: "OrderedDict[Hashable, object]" = OrderedDict()
+        self._parked: List[object] = []
         self._lock = threading.Lock()
 
     def get(self, key, build):
@@ -48,10 +64,15 @@ class _BoundedCache:
             if key in self._d:
                 return self._d[key]
         value = build()
+        for t in _tensors(value):
+            if t.is_cuda:
+                torch.cuda.current_stream(t.device).synchronize()
+                break
         with self._lock:
             if key not in self._d:
                 if len(self._d) >= self.maxsize:
-                    self._d.popitem(last=False)
+                    self._parked.append(self._d.popitem(last=False)[1])
+                    del self._parked[:-self.maxsize]
                 self._d[key] = value
             return self._d[key]
 
@@ -61,6 +82,7 @@ class _BoundedCache:
     def clear(self):
         with self._lock:
             self._d.clear()
+            self._parked.clear()
 
 
 _tables = _BoundedCache(TABLE_CACHE_MAXSIZE)

@@ -10,6 +10,7 @@ file so that it travels with the repo snapshot.
 from __future__ import annotations
 
 import argparse
+import hashlib
 import os
 import shutil
 import subprocess
@@ -36,27 +37,56 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _deps_mtime() -> float:
+def _dep_files():
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
              if f.endswith((".cu", ".cuh", ".inl", ".h"))]
     files.append(os.path.join(os.path.dirname(PKG), "include", "equilib_b200.h"))
-    return max(os.path.getmtime(f) for f in files)
+    return sorted(files)
+
+
+def source_hash() -> str:
+    """sha256 over every source / header the library is built from (names + contents) and
+    the compiler flags: the identity of a build.  It is compiled into the library
+    (eqb_source_hash) so that a shipped .so can be checked against the tree it sits in --
+    modification times say nothing after a checkout, a copy or a snapshot."""
+    h = hashlib.sha256()
+    for f in _dep_files():
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+        h.update(b"\0")
+    h.update(" ".join(ARCH + NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def built_hash() -> str:
+    """The source hash compiled into the existing library ('' if there is none / it predates
+    the hash).  Read from the file, not by loading it."""
+    if not os.path.exists(LIB):
+        return ""
+    with open(LIB, "rb") as fh:
+        blob = fh.read()
+    tag = b"EQB_SRC_HASH="
+    i = blob.find(tag)
+    return blob[i + len(tag):i + len(tag) + 16].decode("ascii", "replace") if i >= 0 else ""
 
 
 def is_fresh() -> bool:
-    return os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime()
+    return built_hash() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB
     nvcc = _nvcc()
+    digest = source_hash()
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
+        tag = [f"-DEQB_SRC_HASH={digest}"] if os.path.basename(src) == "capi.cu" else []
+        cmd = [nvcc, *ARCH, *NVCC_FLAGS, *extra, *tag, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

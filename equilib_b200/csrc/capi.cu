@@ -504,6 +504,17 @@ const char* eqb_last_error(void) { return g_err; }
 
 int64_t eqb_launch_count(void) { return g_launches.load(); }
 
+#define EQB_STR2(x) #x
+#define EQB_STR(x) EQB_STR2(x)
+#ifndef EQB_SRC_HASH
+#define EQB_SRC_HASH
+#endif
+// ("EQB_SRC_HASH=<digest>" is also what build.py::built_hash looks for in the file)
+const char* eqb_source_hash(void) {
+  static const char tagged[] = "EQB_SRC_HASH=" EQB_STR(EQB_SRC_HASH);
+  return tagged + 13;
+}
+
 int32_t eqb_remap(const eqb_remap_desc* d, void* stream) {
   Params p;
   const int rc = fill(d, true, p);

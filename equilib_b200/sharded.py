@@ -69,14 +69,20 @@ def scatter_run_gather(fn: Callable, img: Optional[torch.Tensor], rots: Optional
     """``fn(img, rots, **kwargs)`` for a 4-d batch held by ``root``, computed by all
     ranks of ``group``.  Returns the full result on ``root`` and ``None`` elsewhere.
     Non-root ranks pass ``img=None, rots=None``."""
+    # `rank`, `root` and the partition index are GROUP ranks; point-to-point calls and
+    # broadcast_object_list address processes by GLOBAL rank
     rank = dist.get_rank(group)
     world = dist.get_world_size(group)
+
+    def g(r: int) -> int:
+        return dist.get_global_rank(group, r) if group is not None else r
+
     meta = [None]
     if rank == root:
         assert img is not None and img.dim() == 4 and rots is not None
         assert len(img) == len(rots)
         meta = [(tuple(img.shape), img.dtype, list(rots))]
-    dist.broadcast_object_list(meta, src=root, group=group)
+    dist.broadcast_object_list(meta, src=g(root), group=group)
     shape, dtype, all_rots = meta[0]
     if shape[0] < world:
         raise ValueError(f"batch {shape[0]} is smaller than the group ({world} ranks)")
@@ -92,14 +98,14 @@ def scatter_run_gather(fn: Callable, img: Optional[torch.Tensor], rots: Optional
         reqs = []
         for r, (a, b) in enumerate(parts):
             if r != root and b > a:
-                reqs.append(dist.isend(img[a:b].contiguous(), dst=r, group=group))
+                reqs.append(dist.isend(img[a:b].contiguous(), dst=g(r), group=group))
         local = img[lo:hi]
         for q in reqs:
             q.wait()
     else:
         local = torch.empty((hi - lo,) + tuple(shape[1:]), dtype=dtype, device=dev)
         if hi > lo:
-            dist.recv(local, src=root, group=group)
+            dist.recv(local, src=g(root), group=group)
 
     out_local = fn(local, all_rots[lo:hi], clip_group=group if group is not None else True,
                    **kwargs)
@@ -117,8 +123,8 @@ def scatter_run_gather(fn: Callable, img: Optional[torch.Tensor], rots: Optional
             if r == root:
                 full[a:b] = out_local
             else:
-                dist.recv(full[a:b], src=r, group=group)
+                dist.recv(full[a:b], src=g(r), group=group)
         return full
     if out_local is not None:
-        dist.send(out_local.contiguous(), dst=root, group=group)
+        dist.send(out_local.contiguous(), dst=g(root), group=group)
     return None

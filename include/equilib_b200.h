@@ -219,6 +219,13 @@ int32_t eqb_rotation_compose(const float* trig, int32_t n, float* out);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t eqb_launch_count(void);
 
+/*
+ * Identity of the build: the first 16 hex digits of sha256 over the sources, headers and
+ * compiler flags the library was built from (equilib_b200/build.py::source_hash), "" for a
+ * build made outside build.py.  build() rebuilds when it differs from the tree's.
+ */
+const char* eqb_source_hash(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -599,20 +599,38 @@ def test_launches_are_counted_and_on_current_stream():
 
 
 def test_host_pipeline_matches_direct_call():
+    """The returned host tensor is complete when the call returns (no synchronize here: the
+    pipeline hands completion to the HOST by default), for batches shorter and longer than
+    its ring of device buffers, and with sync=False through the `done` event."""
     from equilib_b200.pipeline import HostPipeline
 
-    frames = torch.from_numpy(cases.noise_image((10, 3, 64, 128), "uint8", 77)).pin_memory()
-    rots = cases.rotation_sweep(13)[3:]
+    frames = torch.from_numpy(cases.noise_image((23, 3, 64, 128), "uint8", 77)).pin_memory()
+    rots = cases.rotation_sweep(26)[3:]
     op = equilib_b200.Equi2Equi(mode="bilinear")
     want = op(frames.to(DEV), rots).cpu()
-    pipe = HostPipeline(op, chunk=4)
-    got = pipe(frames, rots)
-    torch.cuda.synchronize()
+    for chunk, depth in ((4, 3), (2, 2), (32, 3), (1, 4)):
+        pipe = HostPipeline(op, chunk=chunk, depth=depth)
+        got = pipe(frames, rots)
+        assert got.is_pinned() and torch.equal(got, want), (chunk, depth)
+        out = torch.zeros_like(frames).pin_memory()
+        assert pipe(frames, rots, out=out) is out
+        assert torch.equal(out, want)
+        out.zero_()
+        pipe(frames, rots, out=out, sync=False)
+        pipe.done.synchronize()
+        assert torch.equal(out, want)
+
+
+def test_host_views_pipeline_matches_direct_call():
+    from equilib_b200.pipeline import HostViewsPipeline
+
+    equi = torch.from_numpy(cases.band_limited_image((1, 3, 256, 512), "float32", px=96,
+                                                     py=64))[0].to(torch.float16).pin_memory()
+    rots = [{"roll": 0.0, "pitch": 0.3 * math.sin(i), "yaw": 0.4 * i} for i in range(11)]
+    op = equilib_b200.Equi2Pers(96, 128, 90.0)
+    want = op(equi.to(DEV)[None].expand(11, -1, -1, -1), rots).cpu()
+    got = HostViewsPipeline(op, chunk=4)(equi, rots)
     assert got.is_pinned() and torch.equal(got, want)
-    out = torch.empty_like(frames).pin_memory()
-    assert pipe(frames, rots, out=out) is out
-    torch.cuda.synchronize()
-    assert torch.equal(out, want)
 
 
 def test_get_bounding_fov_matches_oracle_perimeter():

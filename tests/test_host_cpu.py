@@ -171,3 +171,24 @@ def test_host_pipeline_chunking():
     assert [list(r) for r in HostPipeline.chunks(10, 4)] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
     assert [list(r) for r in HostPipeline.chunks(3, 4)] == [[0, 1, 2]]
     assert HostPipeline.chunks(0, 4) == []
+
+
+def test_library_carries_the_source_hash_of_this_tree():
+    """build() decides by content, not by modification time: the hash compiled into the
+    library (eqb_source_hash) must be the hash of the sources it sits next to."""
+    from equilib_b200 import build
+
+    assert len(build.source_hash()) == 16
+    assert build.built_hash() == _lib.source_hash()
+    assert _lib.source_hash() == build.source_hash(), "stale libequilib_b200.so: run build()"
+
+
+def test_backend_native_is_an_alias_and_pure_is_rejected():
+    from equilib_b200 import _common
+
+    for b in (None, "b200", "native"):
+        kw = {"backend": b, "cache": object()}
+        _common.check_backend(kw)
+        assert kw == {}
+    with pytest.raises(ValueError):
+        _common.check_backend({"backend": "pure"})

@@ -109,3 +109,34 @@ def _worker_small_batch(rank, world, port):
 
 def test_batch_smaller_than_group_is_rejected():
     mp.spawn(_worker_small_batch, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def _worker_subgroup(rank, world, port):
+    """A strict sub-group {1, 2} of a world of 3: group rank 0 is global rank 1, so any
+    point-to-point call that confuses the two addresses the wrong process."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sub = dist.new_group(ranks=[1, 2])
+        if rank == 0:
+            return
+        g = torch.Generator().manual_seed(1)
+        full = torch.rand((5, 3, 4, 5), generator=g) * 4 - 1
+        rots = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.25 * (i + 1)} for i in range(5)]
+        yaw = torch.tensor([r["yaw"] for r in rots]).view(-1, 1, 1, 1)
+        want = (full * yaw).clamp(full.min(), full.max())  # single-device result
+        is_root = dist.get_rank(sub) == 0  # global rank 1
+        got = sharded.scatter_run_gather(
+            _fake_transform, full if is_root else None, rots if is_root else None,
+            root=0, group=sub, device=torch.device("cpu"))
+        if is_root:
+            assert got is not None and torch.equal(got, want)
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_scatter_gather_over_a_strict_subgroup():
+    mp.spawn(_worker_subgroup, args=(3, _free_port()), nprocs=3, join=True)
