@@ -73,13 +73,18 @@ def u8_diff(a, b):
 # (a) headline shape: 3 x 2048 x 4096 bf16 / uint8 bilinear equi2equi
 # ---------------------------------------------------------------------------------------
 
-# measured on B200 (gpurun_out/parity_rates.jsonl of the round-2 run): see DESIGN.md 2
+# Share of outputs identical to the oracle, per frame (= per rotation), measured on a B200
+# (profiles/r02_parity_rates.jsonl; DESIGN.md 2 tabulates them).  Frame 0 is the IDENTITY
+# rotation: every sampling coordinate is x + 0.5 exactly, every output the mean of two
+# neighbours -- a rounding tie of the 8/16-bit result wherever the neighbours' sum is odd in
+# the last place, so interpolated coordinates (1e-4 px off) flip ~10 % of them by one ulp
+# while the exact chain reproduces the ties.  Bounds: (default path, exact path).
 HEADLINE_BOUNDS = {
-    # (dtype, image): (min share identical, default path; min share identical, exact path)
-    ("bf16", "band"): (0.990, 0.990),
-    ("bf16", "noise"): (0.990, 0.990),
-    ("u8", "band"): (0.985, 0.985),
-    ("u8", "noise"): (0.985, 0.985),
+    # (dtype, image): [(frame 0 = identity), (other frames, worst)]
+    ("bf16", "band"): [(0.890, 0.992), (0.9985, 0.9989)],   # measured .897/.9935, .99966/.99993
+    ("bf16", "noise"): [(0.955, 0.996), (0.9755, 0.9943)],  # measured .959/.9974, .9768/.9954
+    ("u8", "band"): [(0.905, 0.9915), (0.9964, 0.9984)],    # measured .910/.9927, .9974/.9995
+    ("u8", "noise"): [(0.898, 0.993), (0.986, 0.9964)],     # measured .903/.9945, .9871/.9974
 }
 
 
@@ -97,29 +102,27 @@ def test_headline_4k_vs_oracle(dtype, kind):
     out = equilib_b200.equi2equi(x, HEADLINE_ROTS).cpu()
     out_exact = equilib_b200.equi2equi(x, HEADLINE_ROTS, fast_coords=False).cpu()
     assert out.dtype == dtype and out.shape == ref.shape
-    lo_fast, lo_exact = HEADLINE_BOUNDS[(name, kind)]
     if dtype == torch.uint8:
-        d, de = u8_diff(out, ref), u8_diff(out_exact, ref)
-        same, same_e = float((d == 0).float().mean()), float((de == 0).float().mean())
-        within, within_e = float((d <= 1).float().mean()), float((de <= 1).float().mean())
-        record("headline_4k", dtype=name, image=kind, identical_default=same,
-               identical_exact=same_e, within1_default=within, within1_exact=within_e,
-               max_default=int(d.max()), max_exact=int(de.max()))
-        # seam pixels (no interpolation across the seam in the reference) may differ by more
-        assert within >= 0.9999 and within_e >= 0.9999
+        d, de = u8_diff(out, ref).float(), u8_diff(out_exact, ref).float()
+        tol = 1.0
     else:
         d = (out.float() - ref.float()).abs()
         de = (out_exact.float() - ref.float()).abs()
-        same, same_e = float((d == 0).float().mean()), float((de == 0).float().mean())
-        ulp = 2.0 ** -7  # one bf16 ulp of values in [0.5, 1)
-        within = float((d <= ulp * 1.01).float().mean())
-        within_e = float((de <= ulp * 1.01).float().mean())
-        record("headline_4k", dtype=name, image=kind, identical_default=same,
-               identical_exact=same_e, within1ulp_default=within, within1ulp_exact=within_e,
-               max_default=float(d.max()), max_exact=float(de.max()))
-        assert within >= 0.9999 and within_e >= 0.9999
-    assert same >= lo_fast, (same, lo_fast)
-    assert same_e >= lo_exact, (same_e, lo_exact)
+        tol = 2.0 ** -7 * 1.01  # one bf16 ulp of values in [0.5, 1)
+    same = [float((d[i] == 0).float().mean()) for i in range(n)]
+    same_e = [float((de[i] == 0).float().mean()) for i in range(n)]
+    within = float((d <= tol).float().mean())
+    within_e = float((de <= tol).float().mean())
+    record("headline_4k", dtype=name, image=kind,
+           identical_default_per_frame=[round(v, 5) for v in same],
+           identical_exact_per_frame=[round(v, 5) for v in same_e],
+           within_tol_default=within, within_tol_exact=within_e,
+           max_default=float(d.max()), max_exact=float(de.max()))
+    # seam pixels (no interpolation across the seam in the reference) may differ by more
+    assert within >= 0.9999 and within_e >= 0.9999
+    (id_f, id_e), (lo_f, lo_e) = HEADLINE_BOUNDS[(name, kind)]
+    assert same[0] >= id_f and same_e[0] >= id_e, (same[0], same_e[0])
+    assert min(same[1:]) >= lo_f and min(same_e[1:]) >= lo_e, (same, same_e)
 
 
 def test_headline_4k_fp32_vs_oracle():
@@ -198,7 +201,8 @@ def test_config3_cube_w1024_uint8_dice():
     db = u8_diff(back, back_ref)
     record("config3_uint8_dice", e2c_identical=float((d == 0).float().mean()),
            e2c_max=int(d.max()), c2e_identical=float((db == 0).float().mean()), c2e_max=int(db.max()))
-    assert float((d <= 1).float().mean()) >= 0.9999 and float((d == 0).float().mean()) >= 0.985
+    assert float((d <= 1).float().mean()) >= 0.9999
+    assert float((d == 0).float().mean()) >= 0.9933  # measured 0.9944
     assert int(db.max()) == 0
 
 
@@ -226,8 +230,8 @@ def test_config5_multiview_fp16_vs_oracle():
            identical_exact=float((de == 0).float().mean()),
            within1ulp_default=float((d <= ulp * 1.01).float().mean()), max_default=float(d.max()))
     assert float((d <= ulp * 1.01 + 1e-5).float().mean()) >= 0.9999
-    assert float((d == 0).float().mean()) >= 0.97
-    assert float((de == 0).float().mean()) >= 0.97
+    assert float((d == 0).float().mean()) >= 0.996   # measured 0.9973
+    assert float((de == 0).float().mean()) >= 0.9985  # measured 0.9995
 
 
 # ---------------------------------------------------------------------------------------
@@ -248,7 +252,7 @@ def test_config4_pers2equi_1080p_to_8k_uint8_bicubic():
     same_in = float((d[inside] == 0).float().mean()) if bool(inside.any()) else 1.0
     record("config4_pers2equi_8k_u8_bicubic", identical=same, identical_inside_fov=same_in,
            max=int(d.max()), inside_share=float(inside.float().mean()))
-    assert float((d <= 1).float().mean()) >= 0.99999 and same_in >= 0.995
+    assert float((d <= 1).float().mean()) >= 0.99999 and same_in >= 0.9988  # measured 0.9998
 
 
 def test_config4_equi2pers_8k_to_1080p_uint8_bicubic():
@@ -259,7 +263,8 @@ def test_config4_equi2pers_8k_to_1080p_uint8_bicubic():
     d = u8_diff(out, ref)
     record("config4_equi2pers_8k_u8_bicubic", identical=float((d == 0).float().mean()),
            max=int(d.max()))
-    assert float((d <= 1).float().mean()) >= 0.9999 and float((d == 0).float().mean()) >= 0.99
+    assert float((d <= 1).float().mean()) >= 0.9999
+    assert float((d == 0).float().mean()) >= 0.9965  # measured 0.9975
 
 
 # ---------------------------------------------------------------------------------------
@@ -286,7 +291,7 @@ def test_static_remap_4k_vs_oracle(dtype):
     record("static_remap_4k", dtype=str(dtype), identical=same,
            within_tol=float((d <= tol).float().mean()), max=float(d.max()))
     assert float((d <= tol).float().mean()) >= 0.9999
-    assert same >= 0.985
+    assert same >= (0.9925 if dtype == torch.uint8 else 0.9989)  # measured 0.9935 / 0.9999
     # perspective views through a map, against the oracle as well
     sp = equilib_b200.StaticRemap.equi2pers(rots, x.shape, dtype, DEV, 1024, 1024, 90.0)
     ref_p = oracle.equi2pers(img, rots, 1024, 1024, 90.0, mode="bilinear", flavour="cuda")

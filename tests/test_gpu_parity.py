@@ -40,6 +40,24 @@ GOLDEN_CASES = [c for c in cases.golden_cases()]
 MODES = ("nearest", "bilinear", "bicubic")
 
 
+def rate(x, lo):
+    """x >= lo, with x appended to gpurun_out/parity_rates.jsonl under the running test's
+    name -- the bounds below are set ~0.1-0.3 % under the values measured on a B200."""
+    import json
+    import os
+
+    x = float(x)
+    rec = {"test": os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0],
+           "rate": round(x, 6), "bound": lo}
+    try:
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                               "gpurun_out", "parity_rates.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+    return x >= lo
+
+
 def product_run(case, img, kw):
     t = case["transform"]
     kw = dict(kw)
@@ -71,7 +89,7 @@ def compare(case, out, ref):
         d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
         d = np.minimum(d, 256 - d)
         assert np.mean(d <= 1) >= 0.9995  # (seam pixels, see close_except_seam)
-        assert np.mean(d == 0) >= 0.99
+        assert rate(np.mean(d == 0), 0.99)
     else:
         assert close_except_seam(out, ref, 5e-4, 0.9995)
         assert helpers.frac_close(out, ref, rtol=1e-5, atol=2e-5) >= 0.99
@@ -302,15 +320,15 @@ def test_low_precision_images_at_staged_sizes(dtype):
     o, r = out.float().cpu().numpy(), ref.float().numpy()
     d = np.abs(o - r)
     if dtype == torch.uint8:
-        assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.97
+        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
     else:
         ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
         assert close_except_seam(o, r, ulp * 1.01 + 2e-4, 0.99999)
-        assert np.mean(d == 0) >= 0.97
+        assert rate(np.mean(d == 0), 0.97)
     exact = equilib_b200.equi2equi(base.to(DEV), rots, fast_coords=False)
     same = float((exact == out).float().mean())
     print(f"{dtype}: fast == exact for {same:.5f} of outputs")
-    assert same >= 0.97
+    assert rate(same, 0.97)
 
 
 # ---------------------------------------------------------------------------
@@ -381,10 +399,10 @@ def test_16bit_inputs(dtype, ulp, mode):
     assert ref.dtype == dtype
     o, r = out.float().cpu().numpy(), ref.float().numpy()
     if mode == "nearest":
-        assert np.mean(o == r) >= 0.995
+        assert rate(np.mean(o == r), 0.995)
     else:
         assert close_except_seam(o, r, ulp * 1.01 + 2e-4)
-        assert np.mean(o == r) >= 0.98
+        assert rate(np.mean(o == r), 0.98)
 
 
 @pytest.mark.parametrize("odd", [False, True])
@@ -396,7 +414,7 @@ def test_unaligned_output_rows_take_the_scalar_store_path(odd):
     out = equilib_b200.equi2pers(torch.from_numpy(img).to(DEV), rots, 21, w_out, 80.0)
     ref = oracle.equi2pers(torch.from_numpy(img), rots, 21, w_out, 80.0)
     d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-    assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.99
+    assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.99)
 
 
 def test_strided_and_expanded_sources():
@@ -650,7 +668,7 @@ def test_get_bounding_fov_matches_oracle_perimeter():
     want = np.rint(torch.stack(per, dim=1).numpy()).astype(np.int64)
     d = np.abs(got - want)
     d[..., 1] = np.minimum(d[..., 1], W - d[..., 1])  # seam
-    assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.995
+    assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.995)
     one = equilib_b200.get_bounding_fov(equi[0], rots[0], h, w, 90.0)
     assert one.shape == (2 * w + 2 * (h - 2), 2) and np.array_equal(one, got[0])
 
@@ -672,7 +690,7 @@ def test_staged_channel_counts(channels):
     img = torch.from_numpy(cases.band_limited_image((2, channels, 512, 1024), "float32", px=96,
                                                     py=64)).to(torch.bfloat16)
     o, r = _oracle_vs_product("equi2equi", img, HARD_ROTS[1:3])
-    assert close_except_seam(o, r, 2.0 ** -7 * 1.01 + 2e-4, 0.99999) and np.mean(o == r) >= 0.97
+    assert close_except_seam(o, r, 2.0 ** -7 * 1.01 + 2e-4, 0.99999) and rate(np.mean(o == r), 0.97)
 
 
 def test_staged_expanded_batch_single_equirect_many_views():
@@ -693,7 +711,7 @@ def test_staged_expanded_batch_single_equirect_many_views():
     # view looking at the pole); everything else is within one fp16 ulp.
     tol = 2.0 ** -10 * 1.01 + 2e-4
     assert float((d <= tol).float().mean()) >= 0.99999
-    assert float((d == 0).float().mean()) >= 0.97
+    assert rate(float((d == 0).float().mean()), 0.97)
 
 
 def test_staged_sizes_not_multiples_of_the_tile():
@@ -706,10 +724,10 @@ def test_staged_sizes_not_multiples_of_the_tile():
         out = equilib_b200.equi2equi(x.to(DEV), rots, height=503, width=1012)
         ref = oracle.equi2equi(x, rots, height=503, width=1012, flavour="cuda")
         d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-        assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.97
+        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
         exact = equilib_b200.equi2equi(x.to(DEV), rots, height=503, width=1012, fast_coords=False)
         d2 = np.abs(exact.cpu().numpy().astype(int) - ref.numpy().astype(int))
-        assert np.mean(d2 <= 1) >= 0.9999 and np.mean(d2 == 0) >= 0.99
+        assert np.mean(d2 <= 1) >= 0.9999 and rate(np.mean(d2 == 0), 0.99)
 
 
 def test_staged_8k_source_bicubic_uint8():
@@ -720,7 +738,7 @@ def test_staged_8k_source_bicubic_uint8():
     ref = oracle.equi2pers(img, rot, 1080, 1920, 90.0, mode="bicubic", flavour="cuda")
     d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
     d = np.minimum(d, 256 - d)
-    assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.99
+    assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.99)
 
 
 def test_equi2cube_fast_coordinates_faces_of_64():
@@ -732,7 +750,7 @@ def test_equi2cube_fast_coordinates_faces_of_64():
         out = equilib_b200.equi2cube(img.to(DEV), rots, w_face, "dice")
         ref = oracle.equi2cube(img, rots, w_face, "dice", flavour="cuda")
         d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-        assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.97
+        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
 
 
 # --- channels-last uint8 -------------------------------------------------
@@ -758,10 +776,10 @@ def test_channels_last_uint8_in_place(transform, channels):
     assert out.shape == planar.shape and out.is_contiguous(memory_format=torch.channels_last)
     assert not out.is_contiguous()
     d = (out.int() - planar.int()).abs()
-    assert int(d.max()) <= 1 and float((d == 0).float().mean()) >= 0.999
+    assert int(d.max()) <= 1 and rate(float((d == 0).float().mean()), 0.999)
     ref = getattr(oracle, transform)(img, rots, *args, flavour="cuda")
     d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-    assert np.mean(d <= 1) >= 0.9999 and np.mean(d == 0) >= 0.97
+    assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
 
 
 def test_channels_last_ragged_and_pole_tiles():
@@ -774,7 +792,7 @@ def test_channels_last_ragged_and_pole_tiles():
     assert out.is_contiguous(memory_format=torch.channels_last)
     ref = oracle.equi2equi(img, rots, height=516, width=1036, flavour="cuda")
     d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-    assert np.mean(d <= 1) >= 0.9995 and np.mean(d == 0) >= 0.97
+    assert np.mean(d <= 1) >= 0.9995 and rate(np.mean(d == 0), 0.97)
 
 
 def test_channels_last_falls_back_to_planar_where_not_served():
@@ -821,7 +839,7 @@ def test_lean_kernel_random_rotations_match_the_exact_path():
         # one bf16 ulp of values in [0, 1] is 2^-8 at most; seam pixels may flip (see
         # close_except_seam)
         assert float((d <= 2.0 ** -8 * 1.01).float().mean()) >= 0.9999
-        assert float((d == 0).float().mean()) >= 0.995
+        assert rate(float((d == 0).float().mean()), 0.995)
         u8 = (img.float() * 255).to(torch.uint8)
         a = equilib_b200.equi2equi(u8, rots).int()
         b = equilib_b200.equi2equi(u8, rots, fast_coords=False).int()
@@ -849,7 +867,7 @@ def test_static_remap_equals_the_exact_path(dtype, channels):
     d = (out.float() - ref.float()).abs()
     tol = 1.0 if dtype == torch.uint8 else (2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10)
     assert float((d <= tol * 1.01).float().mean()) >= 0.9999
-    assert float((d == 0).float().mean()) >= 0.995
+    assert rate(float((d == 0).float().mean()), 0.995)
     # a second batch through the same map
     img2 = img.flip(3).contiguous()
     assert torch.equal(sr(img2), sr(img2.clone()))
@@ -875,4 +893,4 @@ def test_static_remap_channels_last_uint8(channels):
     assert torch.equal(out, planar)
     ref = equilib_b200.equi2equi(img, rots, fast_coords=False)
     d = (out.int() - ref.int()).abs()
-    assert int(d.max()) <= 1 and float((d == 0).float().mean()) >= 0.99
+    assert int(d.max()) <= 1 and rate(float((d == 0).float().mean()), 0.99)
