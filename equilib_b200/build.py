@@ -24,6 +24,8 @@ LIB = os.path.join(PKG, "libequilib_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--threads", "2"]
+# experiments: extra -D switches (knock-outs, buffer sizes); part of the source hash
+NVCC_FLAGS += os.environ.get("EQB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

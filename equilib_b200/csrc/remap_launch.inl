@@ -188,7 +188,7 @@ static cudaError_t launch_lean2_one(Params p, cudaStream_t stream) {
   const long long tiles_y = (p.dh + kL2TileH - 1) / kL2TileH;
   // tiles per strip: as many as leave >= 4 waves of CTAs (the node prologue amortises over
   // the strip); a strip must not straddle two cube cells
-  const long long wave = 148ll * 7;
+  const long long wave = 148ll * (EQB_L2_BUF_KB > 12 ? 6 : 7);
   int iters = kL2MaxIters;
   while (iters > 1 && ((tiles_x + iters - 1) / iters) * tiles_y * p.B < 4 * wave) iters >>= 1;
   if (XF == EQB_EQUI2CUBE)

@@ -41,6 +41,9 @@
 
 namespace eqb {
 
+#ifndef EQB_L2_BUF_KB
+#define EQB_L2_BUF_KB 12
+#endif
 constexpr int kL2Warps = 4;
 constexpr int kL2TileW = 32, kL2TileH = 16;
 constexpr int kL2Step = 8;                          // node spacing along x
@@ -553,7 +556,10 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7
       continue;
     }
 
-    // ======== general path: exact chain on every pixel; box, or global gathers ==============
+    // ======== general path: taps from the box where they lie inside it, else from global
+    // memory.  Coordinates: interpolated like on the fast path where the tile is smooth and
+    // interior (a footprint too wide for any box -- high source latitudes -- is usually still
+    // smooth), the exact chain elsewhere (source poles, source border, seam, EXACT).
     if (boxed) {
       if (tid == 0) {
         const int k2 = next_boxed(k);
@@ -566,47 +572,82 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7
       const int pitch = boxed ? p.tma_bw[m] : 0;
       const int bh = boxed ? p.tma_bh[m] : 0;
       const T* const box = reinterpret_cast<const T*>(smem_raw + (nbox & 1u) * BUF);
-      RowCtx<XF> rc;
-#pragma unroll 1
-      for (int gy = 0; gy < 2; ++gy) {
-        const int yq = y0q + 2 * gy;
-        if (yq >= p.dh) break;
-        row_setup<XF>(p, b, yq, rc);
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          const int j = 2 * gy + s, x = tile_x0 + xloc(j);
-          if (x >= p.dw) continue;
-          float uj, ui;
-          coords<XF, false>(p, rc, b, x, yq, cell, x - cell * p.w_face, uj, ui);
-          const float ix = to_index(ui, p.inv_wm1, p.swm1f), iy = to_index(uj, p.inv_hm1, p.shm1f);
-          const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
-          const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
-          const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
-          const float w_nw = __fmul_rn(ax, ay), w_ne = __fmul_rn(bx, ay);
-          const float w_sw = __fmul_rn(ax, by), w_se = __fmul_rn(bx, by);
-          const int xi = (int)xf, yi = (int)yf;
-          const int xr = xi - gx0, yr = yi - gy0;
-          const bool from_box = boxed && xr >= 0 && xr <= pitch - 2 && yr >= 0 && yr <= bh - 2;
-          T* d = (gy ? d1 : d0) + (xloc(j) - lx * P);
-          for (int c = 0; c < NC; ++c) {
-            float v_nw, v_ne, v_sw, v_se;
-            if (from_box) {
-              const T* q0 = box + (c * bh + yr) * pitch + xr;
-              v_nw = lds_f(q0); v_ne = lds_f(q0 + 1);
-              v_sw = lds_f(q0 + pitch); v_se = lds_f(q0 + pitch + 1);
-            } else {
-              const T* q0 = src_b + (long long)c * p.ssc + (yi * ssh + xi);
-              if constexpr (ELT == 4) {
-                v_nw = ld_f(q0); v_ne = ld_f(q0 + 1); v_sw = ld_f(q0 + ssh); v_se = ld_f(q0 + ssh + 1);
-              } else {
-                ldg_pair<T>(q0, v_nw, v_ne);
-                ldg_pair<T>(q0 + ssh, v_sw, v_se);
-              }
-            }
-            const T o = OutCvt<T>::cvt(blend4(v_nw, v_ne, v_sw, v_se, w_nw, w_ne, w_sw, w_se),
-                                       p.flags);
-            Pack<T, 1>::st(d + c * p.dsc, &o);
+      const bool interp = !EXACT && (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE)) == L2_SMOOTH;
+      float ixa[4], iya[4];
+      if (interp) {
+        const unsigned long long mone = pk2(-1.0f, -1.0f);
+#pragma unroll
+        for (int g = 0; g < 4 / P; ++g) {
+          const int r = row0 + 2 * ((g * P) >> 1);
+          const int iv = P == 1 ? (lx >> 3) + 2 * (g & 1) : (lx >> 2);
+          const unsigned long long* np =
+              reinterpret_cast<const unsigned long long*>(&nodes[r][k * 4 + iv]);
+          const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+          const unsigned long long d0n = fma2(n1, mone, n0), d2n = fma2(n1, mone, n2),
+                                   d3n = fma2(n1, mone, n3);
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const unsigned long long u =
+                fma2(wt[q][2], d3n, fma2(wt[q][1], d2n, fma2(wt[q][0], d0n, n1)));
+            unpk2(u, ixa[g * P + q], iya[g * P + q]);
           }
+        }
+      } else {
+        RowCtx<XF> rc;
+#pragma unroll 1
+        for (int gy = 0; gy < 2; ++gy) {
+          const int yq = min(y0q + 2 * gy, p.dh - 1);
+          row_setup<XF>(p, b, yq, rc);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int x = min(tile_x0 + xloc(2 * gy + s), p.dw - 1);
+            float uj, ui;
+            coords<XF, false>(p, rc, b, x, yq, cell, x - cell * p.w_face, uj, ui);
+            ixa[2 * gy + s] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[2 * gy + s] = to_index(uj, p.inv_hm1, p.shm1f);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yq = y0q + 2 * (j >> 1), x = tile_x0 + xloc(j);
+        if (yq >= p.dh || x >= p.dw) continue;
+        const float ix = ixa[j], iy = iya[j];
+        const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
+        const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
+        const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
+        const float w_nw = __fmul_rn(ax, ay), w_ne = __fmul_rn(bx, ay);
+        const float w_sw = __fmul_rn(ax, by), w_se = __fmul_rn(bx, by);
+        const int xi = (int)xf, yi = (int)yf;
+        const int xr = xi - gx0, yr = yi - gy0;
+        const bool from_box = boxed && xr >= 0 && xr <= pitch - 2 && yr >= 0 && yr <= bh - 2;
+        T* d = ((j >> 1) ? d1 : d0) + (xloc(j) - lx * P);
+        float v[NC][4];
+        if (from_box) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const T* q0 = box + (c * bh + yr) * pitch + xr;
+            v[c][0] = lds_f(q0); v[c][1] = lds_f(q0 + 1);
+            v[c][2] = lds_f(q0 + pitch); v[c][3] = lds_f(q0 + pitch + 1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {  // (all loads of the pixel in flight together)
+            const T* q0 = src_b + (long long)c * p.ssc + (yi * ssh + xi);
+            if constexpr (ELT == 4) {
+              v[c][0] = ld_f(q0); v[c][1] = ld_f(q0 + 1);
+              v[c][2] = ld_f(q0 + ssh); v[c][3] = ld_f(q0 + ssh + 1);
+            } else {
+              ldg_pair<T>(q0, v[c][0], v[c][1]);
+              ldg_pair<T>(q0 + ssh, v[c][2], v[c][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const T o = OutCvt<T>::cvt(blend4(v[c][0], v[c][1], v[c][2], v[c][3], w_nw, w_ne, w_sw,
+                                            w_se), p.flags);
+          Pack<T, 1>::st(d + c * p.dsc, &o);
         }
       }
     }
