@@ -1,0 +1,746 @@
+// STATUS: EXPERIMENT, NOT BUILT (round 2): remap_lean2.cuh with one TMA box per column half
+// ("split") for tiles whose footprint fits no single box (wide footprints at high source
+// latitudes).  Correct (bit-identical exact path).  32 x 4K bf16, ms per launch:
+//                                   bench   uniform SO(3)   identity   pitch 90
+//   shipped (global gathers there)  1.371      1.645         1.220      1.772
+//   split boxes on the fast path    1.481      1.506         1.303      1.598
+//   split boxes, general path only  1.477      1.558         1.236      1.618
+// Split tiles hold both box buffers, so no box can be prefetched around them: runs of wide
+// tiles near a source pole serialise on the TMA latency (the bench rotations keep the poles in
+// frame, so its 5 % of wide tiles come in runs), while for rotations drawn from SO(3) (13 % of
+// tiles wide) the boxes win.  Not shipped because the headline pattern loses 8 %.
+//
+// remap_lean2_kernel: the round-2 headline kernel -- bilinear, TMA-staged, planar 1 / 3 / 4
+// channels, equi2equi / equi2pers / equi2cube.  Designed from ncu captures of its predecessors
+// (profiles/r01_ncu_remap_bf16_v6_lean_final.txt: 147 instructions per pixel, L1 data pipe
+// 82 %, 2.3 wavefronts per 2-byte tap; profiles/r02_ncu_lean2_v1.txt: 5.3x the source bytes
+// fetched as TMA boxes, a fifth of all issued instructions spinning on the box barrier):
+//
+//  1. COORDINATES FROM A STRIP-WIDE NODE GRID.  A CTA walks a strip of up to 8 tiles
+//     (32 x 16 pixels each) along x.  Before the first tile all 128 threads evaluate the
+//     exact coordinate chain at the strip's NODES -- every 8th column of every row, plus one
+//     column on either side -- into shared memory (fully occupied warps: 1/8 node per pixel
+//     instead of the 1/4 of round 1, where every lane computed its own).  A pixel then gets
+//     (ui, uj) from the four nodes around it on its own row by cubic Lagrange interpolation
+//     with weights that are LANE CONSTANTS (a lane's pixels all sit at the same offset inside
+//     their 8-pixel interval), as differences from the nearest node: 4 LDS.64 + 3 packed
+//     subtractions + 3 FFMA2 per pixel, no shuffles, no weight loads.
+//  2. PER-TILE HEADERS.  The same prologue reduces each tile's node hull to its TMA box
+//     (origin, shape) and to flags -- smooth (4th and 2nd differences of the nodes small: the
+//     interpolation error is below 1e-3 px and no pixel leaves the node hull by more than
+//     1/4 px, so no per-pixel "inside the box" test is needed), border (a clamp, the wrap or
+//     the footprint shift at the last column could trigger), seam.  Smooth interior tiles
+//     with a box take a straight-line fast path: no reductions, votes, clamps or wraps.
+//  3. SQUARER TILES, TWO BOX BUFFERS.  A 32 x 16 tile of a view rolled by 0.3 rad needs a
+//     48 x 30 box where the 64 x 8 tile of round 1 needed 96 x 40: less than half the L2 ->
+//     shared traffic per pixel.  The box of the NEXT tile is requested while the current one
+//     is blended (two buffers, full / empty mbarriers per buffer, no __syncthreads in the tile
+//     loop, waits back off with nanosleep instead of spinning on the issue slots).
+//  4. ALIGNED-WORD TAPS.  The 16 lanes of a row read 16 ADJACENT source pixels per tap
+//     instruction.  A 1- or 2-byte tap is fetched as the aligned 32-bit word that holds it
+//     (lanes sharing a word read the same address: a broadcast, one wavefront) and moved
+//     into place by one PRMT with a per-pixel selector -- the same two instructions as
+//     LDS.U16 + shift, without the extra wavefronts of sub-word accesses (measured: 1.7 per
+//     LDS.U16 when neighbouring lanes read the two halves of one word).
+//
+// Tiles that are not smooth (source poles), border / seam / ragged tiles and the EXACT variant
+// evaluate the exact chain on every pixel; tiles whose footprint fits no box (poles, seam)
+// gather from global memory -- same values on every path
+// (tests: test_staged_and_direct_kernels_agree).
+#pragma once
+
+#include "remap_kernels.cuh"
+
+namespace eqb {
+
+#ifndef EQB_L2_SPLIT
+#define EQB_L2_SPLIT 1  // experiments: 0 = no per-half boxes for wide tiles
+#endif
+constexpr int kL2Warps = 4;
+constexpr int kL2TileW = 32, kL2TileH = 16;
+constexpr int kL2Step = 8;                          // node spacing along x
+constexpr int kL2MaxIters = 8;                      // tiles per strip
+constexpr int kL2Cols = kL2MaxIters * 4 + 3;        // node columns -1 .. 4 * iters + 1
+constexpr int kL2Boxes = 11;
+constexpr int kL2MinBoxH = kL2TileH + 5;            // an upright tile: 16 rows + 1 + margins
+static_assert(kL2Boxes <= kTmaSlots, "tensor-map slots");
+
+// One box buffer (a CTA holds two).
+EQB_HD constexpr int l2_buf_bytes(int elt) { return elt == 4 ? 16 * 1024 : 12 * 1024; }
+
+// Box m: l2_box_w x l2_box_h source pixels x channels.  Boxes 0-1 are small (upright and
+// mildly rolled views); the others spend the whole buffer in different aspect ratios: 48
+// wide for rolls, 64-96 for the longitude stretch 1 / cos(lat) at high source latitudes,
+// 40 / 32 for rolls beyond 45 degrees.  pick = the first that fits.
+EQB_HD constexpr int l2_box_w(int elt, int m) {
+  const int w = m <= 2 ? 48 : m == 3 ? 64 : m == 4 ? 56 : m == 5 ? 80 : m == 6 ? 72 :
+                m == 7 ? 88 : m == 8 ? 96 : m == 9 ? 40 : 32;
+  const int per16 = 16 / elt;
+  return (w + per16 - 1) / per16 * per16;
+}
+EQB_HD constexpr int l2_box_h(int elt, int nc, int m) {
+  const int budget = l2_buf_bytes(elt) / elt / nc;
+  const int full = budget / l2_box_w(elt, m) < 128 ? budget / l2_box_w(elt, m) : 128;
+  const int small = m == 0 ? 24 : 32;
+  return m < 2 && small < full ? small : full;
+}
+
+// Cubic Lagrange weights of the nodes at -8, 0, +8, +16 for the pixel at offset t (0..7)
+// from the second one; the weight of that node is not stored (the weights sum to 1:
+// u = n1 + sum w_j (n_j - n1)).
+struct L2Weights { float w[8][3]; };
+constexpr L2Weights make_l2_weights() {
+  L2Weights r{};
+  for (int t = 0; t < 8; ++t) {
+    const double s = t / 8.0;
+    r.w[t][0] = (float)(-s * (s - 1.0) * (s - 2.0) / 6.0);
+    r.w[t][1] = (float)(-(s + 1.0) * s * (s - 2.0) / 2.0);
+    r.w[t][2] = (float)((s + 1.0) * s * (s - 1.0) / 6.0);
+  }
+  return r;
+}
+static __device__ const L2Weights g_l2_weights = make_l2_weights();
+
+enum : int { L2_SMOOTH = 1, L2_BORDER = 2, L2_STRADDLE = 4, L2_RAGGED = 8, L2_BACKGROUND = 16,
+              L2_SPLIT = 32 };
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Wait that yields the issue slots: one probe, then probes 32 ns apart.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(32);
+  }
+}
+
+// Rays of the cube faces as coded in torch_utils/grid.py:137-171 (F R B L U D).
+__device__ __forceinline__ void cube_ray(int face, float rc, float rr, float& mx, float& my,
+                                         float& mz) {
+  switch (face) {
+    case 0: mx = 0.5f; my = rc; mz = -rr; break;
+    case 1: mx = -rc; my = 0.5f; mz = -rr; break;
+    case 2: mx = -0.5f; my = -rc; mz = -rr; break;
+    case 3: mx = rc; my = -0.5f; mz = -rr; break;
+    case 4: mx = rr; my = rc; mz = 0.5f; break;
+    default: mx = -rr; my = rc; mz = -0.5f; break;
+  }
+}
+
+// Coordinates of a NODE: column x may lie up to 8 pixels outside the image (the map is
+// continued smoothly: longitude is periodic, the pinhole grid and the cube-face ramp are
+// linear).  Nodes only feed the interpolation and the boxes, never a pixel directly -- except
+// where x is a pixel column, and there this is the exact chain.
+template <int XF>
+__device__ __forceinline__ void node_coords(const Params& p, const RowCtx<XF>& c, int x, int y,
+                                            int cell, float& uj, float& ui) {
+  if (XF == EQB_EQUI2EQUI) {
+    const int xw = x < 0 ? x + p.dw : (x >= p.dw ? x - p.dw : x);
+    coords<XF, false>(p, c, 0, xw, y, 0, 0, uj, ui);
+  } else if (XF == EQB_EQUI2PERS) {
+    coords<XF, false>(p, c, 0, x, y, 0, 0, uj, ui);
+  } else {  // EQB_EQUI2CUBE
+    const int w = p.w_face, lx = x - cell * w;
+    float rcol;
+    if (lx >= 0 && lx < w) {
+      rcol = __ldg(p.tx + lx);
+    } else {
+      const float step = __ldg(p.tx + 1) - __ldg(p.tx);
+      rcol = lx < 0 ? fmaf((float)lx, step, __ldg(p.tx))
+                    : fmaf((float)(lx - (w - 1)), step, __ldg(p.tx + w - 1));
+    }
+    float mx, my, mz, X, Y, Z, phi, theta;
+    cube_ray(cell, rcol, c.r0, mx, my, mz);
+    rotate(c.A, mx, my, mz, X, Y, Z);
+    spherical<false>(X, Y, Z, phi, theta);
+    tail_minus_half<false>(phi, theta, p.shf, p.swf, uj, ui);
+  }
+}
+
+// ---- taps --------------------------------------------------------------------------------
+// Sampling state of one pixel on the fast path: the word addresses of its left and right taps
+// (row y0, channel 0) and the PRMT selectors that move the tap out of its word.
+struct L2Px {
+  unsigned a0, a1;  // shared-memory byte addresses
+  unsigned s0, s1;  // PRMT selectors (fp16 / fp32: unused)
+};
+
+template <typename T>
+__device__ __forceinline__ void l2_px_setup(unsigned a, L2Px& q) {
+  if (sizeof(T) == 2 && !cuda::std::is_same<T, __half>::value) {
+    // bf16 -> fp32 is "the 16 bits in the upper half": selector 0x1044 lifts the low half of
+    // the word ([0, 0, b0, b1]), 0x3244 keeps the high half ([0, 0, b2, b3])
+    q.a0 = a & ~3u;
+    q.a1 = (a + 2u) & ~3u;
+    q.s0 = (a & 2u) ? 0x3244u : 0x1044u;
+    q.s1 = q.s0 ^ 0x2200u;
+  } else if (sizeof(T) == 1) {
+    // byte k of the word into byte 0 of 0x4B0000kk = 2^23 + k
+    q.a0 = a & ~3u;
+    q.a1 = (a + 1u) & ~3u;
+    q.s0 = 0x7540u | (a & 3u);
+    q.s1 = 0x7540u | ((a + 1u) & 3u);
+  } else {
+    q.a0 = a;
+    q.a1 = a + (unsigned)sizeof(T);
+    q.s0 = q.s1 = 0u;
+  }
+}
+
+// The tap at compile-time byte offset OFF (row / channel) from word address `addr`.
+template <typename T, int OFF>
+__device__ __forceinline__ float l2_tap(unsigned addr, unsigned sel) {
+  if (sizeof(T) == 4) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+  }
+  if (cuda::std::is_same<T, __half>::value) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(OFF));
+    return __half2float(__ushort_as_half(v));
+  }
+  unsigned w;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w) : "r"(addr), "n"(OFF));
+  if (sizeof(T) == 1)
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 8388608.0f);
+  return __uint_as_float(__byte_perm(w, 0u, sel));
+}
+
+// Store of a lane's four results of one channel: d0 / d1 point at its pixels of the upper /
+// lower of its two rows.  2- and 4-byte types: pixels d[0], d[16]; uint8: the pair d[0..1].
+template <typename T>
+__device__ __forceinline__ void l2_store(T* d0, T* d1, const float (&o)[4], bool row1) {
+  if constexpr (sizeof(T) == 4) {
+    __stcs(reinterpret_cast<float*>(d0), o[0]);
+    __stcs(reinterpret_cast<float*>(d0) + 16, o[1]);
+    if (row1) {
+      __stcs(reinterpret_cast<float*>(d1), o[2]);
+      __stcs(reinterpret_cast<float*>(d1) + 16, o[3]);
+    }
+  } else if constexpr (sizeof(T) == 2) {
+    unsigned lo, hi;
+    if constexpr (cuda::std::is_same<T, __half>::value) {
+      const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+      lo = *reinterpret_cast<const unsigned*>(&a);
+      hi = *reinterpret_cast<const unsigned*>(&b);
+    } else {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(o[2], o[3]);
+      lo = *reinterpret_cast<const unsigned*>(&a);
+      hi = *reinterpret_cast<const unsigned*>(&b);
+    }
+    unsigned short* q0 = reinterpret_cast<unsigned short*>(d0);
+    unsigned short* q1 = reinterpret_cast<unsigned short*>(d1);
+    __stcs(q0, (unsigned short)lo);
+    __stcs(q0 + 16, (unsigned short)(lo >> 16));
+    if (row1) {
+      __stcs(q1, (unsigned short)hi);
+      __stcs(q1 + 16, (unsigned short)(hi >> 16));
+    }
+  } else {
+    // bilinear code values are convex combinations: floor == the reference's truncation
+    const unsigned t0 = u8_floor_bits(o[0]), t1 = u8_floor_bits(o[1]);
+    const unsigned t2 = u8_floor_bits(o[2]), t3 = u8_floor_bits(o[3]);
+    __stcs(reinterpret_cast<unsigned short*>(d0), (unsigned short)__byte_perm(t0, t1, 0x0040u));
+    if (row1)
+      __stcs(reinterpret_cast<unsigned short*>(d1), (unsigned short)__byte_perm(t2, t3, 0x0040u));
+  }
+}
+
+// Blend + store of one channel from box M: pixel pairs (0, 1) and (2, 3) share FFMA2s.
+template <typename T, int M, int NC, int CI>
+__device__ __forceinline__ void l2_blend_channel(const L2Px (&q)[4],
+                                                 const unsigned long long (&w_nw)[2],
+                                                 const unsigned long long (&w_ne)[2],
+                                                 const unsigned long long (&w_sw)[2],
+                                                 const unsigned long long (&w_se)[2], T* d0,
+                                                 T* d1, long long dsc, bool row1) {
+  constexpr int ELT = (int)sizeof(T);
+  constexpr int ROW = l2_box_w(ELT, M) * ELT;
+  constexpr int CH = CI * ROW * l2_box_h(ELT, NC, M);
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const L2Px &x = q[2 * k], &y = q[2 * k + 1];
+    unsigned long long acc =
+        mul2(pk2(l2_tap<T, CH>(x.a0, x.s0), l2_tap<T, CH>(y.a0, y.s0)), w_nw[k]);
+    acc = fma2(pk2(l2_tap<T, CH>(x.a1, x.s1), l2_tap<T, CH>(y.a1, y.s1)), w_ne[k], acc);
+    acc = fma2(pk2(l2_tap<T, CH + ROW>(x.a0, x.s0), l2_tap<T, CH + ROW>(y.a0, y.s0)), w_sw[k], acc);
+    acc = fma2(pk2(l2_tap<T, CH + ROW>(x.a1, x.s1), l2_tap<T, CH + ROW>(y.a1, y.s1)), w_se[k], acc);
+    unpk2(acc, o[2 * k], o[2 * k + 1]);
+  }
+  l2_store<T>(d0 + CI * dsc, d1 + CI * dsc, o, row1);
+}
+
+template <typename T, int M, int NC>
+__device__ __forceinline__ void l2_blend(const L2Px (&q)[4], const float (&fx)[4],
+                                         const float (&fy)[4], T* d0, T* d1, long long dsc,
+                                         bool row1) {
+  const unsigned long long one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
+  unsigned long long w_nw[2], w_ne[2], w_sw[2], w_se[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const unsigned long long bx = pk2(fx[2 * k], fx[2 * k + 1]), by = pk2(fy[2 * k], fy[2 * k + 1]);
+    const unsigned long long ax = fma2(bx, mone, one), ay = fma2(by, mone, one);  // 1 - b, exact
+    w_nw[k] = mul2(ax, ay);
+    w_ne[k] = mul2(bx, ay);
+    w_sw[k] = mul2(ax, by);
+    w_se[k] = mul2(bx, by);
+  }
+  l2_blend_channel<T, M, NC, 0>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+  if constexpr (NC > 1) l2_blend_channel<T, M, NC, 1>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+  if constexpr (NC > 2) l2_blend_channel<T, M, NC, 2>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+  if constexpr (NC > 3) l2_blend_channel<T, M, NC, 3>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
+}
+
+template <int XF, typename T, int NC, bool EXACT>
+__global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7)
+    remap_lean2_kernel(const __grid_constant__ Params p) {
+  constexpr int ELT = (int)sizeof(T);
+  constexpr int PER16 = 16 / ELT;
+  constexpr int P = ELT == 1 ? 2 : 1;  // adjacent pixels per lane and row: a group is >= 2 bytes
+  constexpr int BUF = l2_buf_bytes(ELT);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // two box buffers
+  __shared__ __align__(16) float2 nodes[kL2TileH][kL2Cols + 1];  // (ui, uj)
+  __shared__ __align__(16) int4 headers[kL2MaxIters];
+  __shared__ __align__(8) int2 origin_r[kL2MaxIters];  // split tiles: origin of the right half's box
+  __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int tile_y0 = blockIdx.y * kL2TileH;
+  const int strip_x0 = blockIdx.x * p.iters * kL2TileW;
+  const int ntiles = min(p.iters, (p.dw - strip_x0 + kL2TileW - 1) / kL2TileW);
+  int cell = 0;
+  if (XF == EQB_EQUI2CUBE) cell = strip_x0 / p.w_face;  // (a strip never straddles two cells)
+  const bool background = XF == EQB_EQUI2CUBE && cell >= 6;
+
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], kL2Warps);
+    mbar_init(&empty_bar[1], kL2Warps);
+  }
+
+  // ---- prologue 1: the exact chain at the strip's nodes -------------------------------
+  if (!background) {
+    const int row = tid & (kL2TileH - 1);
+    const int y = min(tile_y0 + row, p.dh - 1);
+    RowCtx<XF> rc;
+    row_setup<XF>(p, b, y, rc);
+    const int ncols = ntiles * 4 + 3;
+    for (int col = tid >> 4; col < ncols; col += kL2Warps * 32 / kL2TileH) {
+      float uj, ui;
+      node_coords<XF>(p, rc, strip_x0 + kL2Step * (col - 1), y, cell, uj, ui);
+      nodes[row][col] = make_float2(ui, uj);
+    }
+  }
+  __syncthreads();
+
+  // ---- prologue 2: one header per tile (warp w: tiles w, w + 4) -------------------------
+  {
+    // lane m holds the shape of box m
+    const int my_box = lane < kL2Boxes ? (p.tma_bw[lane & 15] | (p.tma_bh[lane & 15] << 16)) : 0;
+    for (int k = warp; k < ntiles; k += kL2Warps) {
+      int flags = 0;
+      if (strip_x0 + (k + 1) * kL2TileW > p.dw || tile_y0 + kL2TileH > p.dh) flags |= L2_RAGGED;
+      if (background) {
+        if (lane == 0) headers[k] = make_int4(0, 0, -1, flags | L2_BACKGROUND);
+        continue;
+      }
+      // window of five nodes centred on tile-local node column c = 1 or 3 of row r: the
+      // tile's own columns are 0..4, the windows also see -1 and 5 (interpolation stencils)
+      const int r = lane & 15, c = 1 + 2 * (lane >> 4);
+      const float2* np = &nodes[r][k * 4 + c - 1];  // (array index = node column + 1)
+      float2 n[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) n[i] = np[i];
+      float ulo = fminf(fminf(n[1].x, n[2].x), n[3].x), uhi = fmaxf(fmaxf(n[1].x, n[2].x), n[3].x);
+      float vlo = fminf(fminf(n[1].y, n[2].y), n[3].y), vhi = fmaxf(fmaxf(n[1].y, n[2].y), n[3].y);
+      const float2 e = c == 1 ? n[4] : n[0];  // the end node that is a column of the tile
+      ulo = fminf(ulo, e.x); uhi = fmaxf(uhi, e.x);
+      vlo = fminf(vlo, e.y); vhi = fmaxf(vhi, e.y);
+      const float2 f = c == 1 ? n[0] : n[4];  // the one outside
+      const float alo = fminf(ulo, f.x), ahi = fmaxf(uhi, f.x);
+      // (coordinates are >= 0: their bit patterns order like integers)
+      const float umin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(ulo)));
+      const float umax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(uhi)));
+      const float vmin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(vlo)));
+      const float vmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(vhi)));
+      const float amin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(alo)));
+      const float amax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(ahi)));
+      // the tile's own footprint wraps around the seam (no single box holds it) / some node of
+      // its interpolation stencils lies across the seam (such tiles take the exact chain)
+      const bool box_straddle = umax - umin >= 0.5f * p.swf;
+      const bool straddle = amax - amin >= 0.5f * p.swf;
+      // smoothness: 4th difference (the cubic's error is ~0.023 of it) and 2nd difference (a
+      // pixel leaves the hull of its neighbouring nodes by at most 1/8 of it), from differences
+      // against the centre node (no cancellation at coordinates of order 4096)
+      bool ok = !straddle;
+      {
+        const float ax = n[0].x - n[2].x, bx = n[1].x - n[2].x, cx = n[3].x - n[2].x,
+                    dx = n[4].x - n[2].x;
+        const float ay = n[0].y - n[2].y, by = n[1].y - n[2].y, cy = n[3].y - n[2].y,
+                    dy = n[4].y - n[2].y;
+        const float d4x = (ax + dx) - 4.0f * (bx + cx), d4y = (ay + dy) - 4.0f * (by + cy);
+        const float d2x = bx + cx, d2y = by + cy;
+        ok = ok && fmaxf(fabsf(d4x), fabsf(d4y)) < 0.03f && fmaxf(fabsf(d2x), fabsf(d2y)) < 1.5f;
+      }
+      if (__all_sync(0xffffffffu, ok)) flags |= L2_SMOOTH;
+      if (straddle) flags |= L2_STRADDLE;
+      if (umin < 1.0f || umax > p.swm1f - 2.0f || vmin < 1.0f || vmax > p.shm1f - 2.0f)
+        flags |= L2_BORDER;
+      // box: top-left taps of the hull (with the footprint shift at the last column / row),
+      // one more pixel right and down, margin 2
+      const int bx0 = (int)fminf(floorf(fminf(umin, p.swm1f)), p.swm1f - 1.0f);
+      const int bx1 = (int)fminf(floorf(fminf(umax, p.swm1f)), p.swm1f - 1.0f);
+      const int by0 = (int)fminf(floorf(fminf(vmin, p.shm1f)), p.shm1f - 1.0f);
+      const int by1 = (int)fminf(floorf(fminf(vmax, p.shm1f)), p.shm1f - 1.0f);
+      const int gx0 = (bx0 - 2) & ~(PER16 - 1);  // 16-byte aligned (TMA requirement)
+      const int gy0 = by0 - 2;
+      const int need_w = bx1 + 4 - gx0, need_h = by1 + 4 - gy0;
+      const unsigned fit = __ballot_sync(
+          0xffffffffu, need_w <= (my_box & 0xffff) && need_h <= (my_box >> 16));
+      int m = (box_straddle || !p.use_tma) ? -1 : __ffs(fit) - 1;
+      int hx = gx0, hy = gy0;
+      if (EQB_L2_SPLIT && P == 1 && m < 0 && p.use_tma) {
+        // no box holds the tile (wide footprints at high source latitudes, the seam): one box
+        // per column half -- pixel slot 0 of every lane lies in the left half, slot 1 in the
+        // right one -- of one common shape (the tap offsets are compile-time per shape).
+        // Lanes 0-15 (c = 1) hold the hull of columns 0 1 2 3, lanes 16-31 of columns 1 2 3 4:
+        // the halves need columns 0 1 2 / 2 3 4.
+        const float ul = fminf(fminf(n[1].x, n[2].x), n[3].x), uh = fmaxf(fmaxf(n[1].x, n[2].x), n[3].x);
+        const float vl = fminf(fminf(n[1].y, n[2].y), n[3].y), vh = fmaxf(fmaxf(n[1].y, n[2].y), n[3].y);
+        const float big = 3.0e38f;
+        const bool left = lane < 16;
+        int gxs[2], gys[2], nw = 0, nh = 0;
+        bool bad = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool mine = left == (h == 0);
+          const float u0 = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(mine ? ul : big)));
+          const float u1 = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(mine ? uh : 0.0f)));
+          const float v0 = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(mine ? vl : big)));
+          const float v1 = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(mine ? vh : 0.0f)));
+          bad = bad || (u1 - u0 >= 0.5f * p.swf);
+          const int ax0 = (int)fminf(floorf(fminf(u0, p.swm1f)), p.swm1f - 1.0f);
+          const int ax1 = (int)fminf(floorf(fminf(u1, p.swm1f)), p.swm1f - 1.0f);
+          const int ay0 = (int)fminf(floorf(fminf(v0, p.shm1f)), p.shm1f - 1.0f);
+          const int ay1 = (int)fminf(floorf(fminf(v1, p.shm1f)), p.shm1f - 1.0f);
+          gxs[h] = (ax0 - 2) & ~(PER16 - 1);
+          gys[h] = ay0 - 2;
+          nw = max(nw, ax1 + 4 - gxs[h]);
+          nh = max(nh, ay1 + 4 - gys[h]);
+        }
+        const unsigned fit2 = __ballot_sync(
+            0xffffffffu, nw <= (my_box & 0xffff) && nh <= (my_box >> 16));
+        if (!bad && fit2) {
+          m = __ffs(fit2) - 1;
+          flags |= L2_SPLIT;
+          hx = gxs[0];
+          hy = gys[0];
+          if (lane == 0) origin_r[k] = make_int2(gxs[1], gys[1]);
+        }
+      }
+      if (lane == 0) headers[k] = make_int4(hx, hy, m, flags);
+    }
+  }
+  __syncthreads();
+
+  // ---- tile loop ---------------------------------------------------------------------------
+  // lane (lx, ly) of warp w owns, in rows 4w + ly and 4w + ly + 2, the pixels lx and lx + 16
+  // (uint8: the pair 2 lx, 2 lx + 1).  Pixel j: row j >> 1, column slot j & 1.
+  const int lx = lane & 15, ly = lane >> 4;
+  const int row0 = warp * 4 + ly;
+  const int y0q = tile_y0 + row0;
+  const bool row0_ok = y0q < p.dh, row1_ok = y0q + 2 < p.dh;
+  const unsigned tile_s = smem_u32(smem_raw);
+  const T* const src_b = static_cast<const T*>(p.src) + (long long)b * p.ssb;
+  T* const dst_b = static_cast<T*>(p.dst) + (long long)b * p.dsb;
+  const int ssh = (int)p.ssh;
+  auto xloc = [&](int j) { return P == 1 ? lx + 16 * (j & 1) : 2 * lx + (j & 1); };
+  // interpolation weights of this lane's pixels (offset t inside their 8-pixel interval)
+  unsigned long long wt[P][3];
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const int t = (lx * P + q) & 7;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wt[q][j] = pk2(g_l2_weights.w[t][j], g_l2_weights.w[t][j]);
+  }
+
+  // The box of boxed tile n lives in buffer n & 1; phase parity of its barriers (n >> 1) & 1.
+  // Thread 0 requests the box of the NEXT boxed tile while the current one is blended.
+  // A split tile (L2_SPLIT; general path only) takes two consecutive sequence numbers: its
+  // left box n, its right box n + 1 (requested at the top of the tile itself: its buffer is the
+  // previous tile's).
+  auto issue_at = [&](int m, int gx, int gy, unsigned n) {  // thread 0 only
+    const unsigned buf = n & 1u;
+    if (n >= 2) mbar_wait_backoff(&empty_bar[buf], ((n >> 1) - 1u) & 1u);
+    mbar_expect_tx(&full_bar[buf], (unsigned)(p.tma_bw[m] * p.tma_bh[m] * NC * ELT));
+    tma_load_box(smem_raw + buf * BUF, &p.tmaps[m], &full_bar[buf], gx, gy, 0,
+                 p.tma_batched ? b : 0);
+  };
+  auto issue = [&](int k, unsigned n) {  // thread 0 only: the (first) box of tile k
+    const int4 h = headers[k];
+    issue_at(h.z, h.x, h.y, n);
+  };
+  auto next_boxed = [&](int k) {
+    for (++k; k < ntiles; ++k)
+      if (headers[k].z >= 0) return k;
+    return -1;
+  };
+  unsigned nbox = 0;
+  if (tid == 0) {
+    const int k0 = next_boxed(-1);
+    if (k0 >= 0) issue(k0, 0);
+  }
+
+  for (int k = 0; k < ntiles; ++k) {
+    const int4 hdr = headers[k];
+    const int gx0 = hdr.x, gy0 = hdr.y, m = hdr.z, flags = hdr.w;
+    const int tile_x0 = strip_x0 + k * kL2TileW;
+    const bool boxed = m >= 0;
+    T* d0 = dst_b + (long long)min(y0q, p.dh - 1) * p.dsh + tile_x0 + lx * P;
+    if (XF == EQB_EQUI2CUBE)
+      d0 = dst_b + (long long)min(y0q, p.dh - 1) * p.dsh + p.cell_off[cell] +
+           (tile_x0 - cell * p.w_face) + lx * P;
+    T* d1 = d0 + 2 * p.dsh;
+
+    if (flags & L2_BACKGROUND) {  // dice background cell
+      if (row0_ok) {
+        const float z[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < NC; ++c) l2_store<T>(d0 + c * p.dsc, d1 + c * p.dsc, z, row1_ok);
+      }
+      continue;
+    }
+
+    const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED | L2_SPLIT)) == L2_SMOOTH
+                                      : (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE |
+                                                  L2_RAGGED | L2_SPLIT)) == L2_SMOOTH);
+    if (fast) {
+      // ======== fast path: smooth tile with a box ==========================================
+      float ixa[4], iya[4];
+      if constexpr (!EXACT) {
+        const unsigned long long mone = pk2(-1.0f, -1.0f);
+#pragma unroll
+        for (int g = 0; g < 4 / P; ++g) {
+          // P == 1: pixel g; P == 2: the pair (2g, 2g + 1) shares its stencil
+          const int r = row0 + 2 * ((g * P) >> 1);
+          const int iv = P == 1 ? (lx >> 3) + 2 * (g & 1) : (lx >> 2);
+          const unsigned long long* np =
+              reinterpret_cast<const unsigned long long*>(&nodes[r][k * 4 + iv]);
+          const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+          const unsigned long long d0n = fma2(n1, mone, n0), d2n = fma2(n1, mone, n2),
+                                   d3n = fma2(n1, mone, n3);
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const unsigned long long u =
+                fma2(wt[q][2], d3n, fma2(wt[q][1], d2n, fma2(wt[q][0], d0n, n1)));
+            unpk2(u, ixa[g * P + q], iya[g * P + q]);
+          }
+        }
+      } else {
+        RowCtx<XF> rc;
+#pragma unroll
+        for (int gy = 0; gy < 2; ++gy) {
+          const int y = min(y0q + 2 * gy, p.dh - 1);
+          row_setup<XF>(p, b, y, rc);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int j = 2 * gy + s, x = tile_x0 + xloc(j);
+            float uj, ui;
+            coords<XF, false>(p, rc, b, x, y, cell, x - cell * p.w_face, uj, ui);
+            ixa[j] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[j] = to_index(uj, p.inv_hm1, p.shm1f);
+          }
+        }
+      }
+      L2Px px[4];
+      float fx[4], fy[4];
+      {
+        const int pitch = p.tma_bw[m];
+        const float pitchf = (float)pitch;
+        // byte address = ((yf - gy0) * pitch + (xf - gx0)) * ELT + buffer; yf * pitch + xf is
+        // an exact integer below 2^24
+        const int base = (int)(tile_s + (nbox & 1u) * BUF) - (gy0 * pitch + gx0) * ELT;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float xf = floorf(ixa[j]), yf = floorf(iya[j]);
+          if (EXACT) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
+            xf = fminf(xf, p.swm1f - 1.0f);
+            yf = fminf(yf, p.shm1f - 1.0f);
+          }
+          fx[j] = __fsub_rn(ixa[j], xf);
+          fy[j] = __fsub_rn(iya[j], yf);
+          l2_px_setup<T>((unsigned)((int)fmaf(yf, pitchf, xf) * ELT + base), px[j]);
+        }
+      }
+      // request the next box, then wait for this one
+      if (tid == 0) {
+        const int k2 = next_boxed(k);
+        if (k2 >= 0) issue(k2, nbox + 1);
+      }
+      __syncwarp();
+      mbar_wait_backoff(&full_bar[nbox & 1u], (nbox >> 1) & 1u);
+      if (row0_ok) {
+        auto blend_m = [&](auto mc) {
+          constexpr int M = decltype(mc)::value;
+          l2_blend<T, M, NC>(px, fx, fy, d0, d1, p.dsc, row1_ok);
+        };
+        switch (m) {
+          case 0: blend_m(cuda::std::integral_constant<int, 0>{}); break;
+          case 1: blend_m(cuda::std::integral_constant<int, 1>{}); break;
+          case 2: blend_m(cuda::std::integral_constant<int, 2>{}); break;
+          case 3: blend_m(cuda::std::integral_constant<int, 3>{}); break;
+          case 4: blend_m(cuda::std::integral_constant<int, 4>{}); break;
+          case 5: blend_m(cuda::std::integral_constant<int, 5>{}); break;
+          case 6: blend_m(cuda::std::integral_constant<int, 6>{}); break;
+          case 7: blend_m(cuda::std::integral_constant<int, 7>{}); break;
+          case 8: blend_m(cuda::std::integral_constant<int, 8>{}); break;
+          case 9: blend_m(cuda::std::integral_constant<int, 9>{}); break;
+          default: blend_m(cuda::std::integral_constant<int, 10>{}); break;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[nbox & 1u]);
+      ++nbox;
+      continue;
+    }
+
+    // ======== general path: taps from the box where they lie inside it, else from global
+    // memory.  Coordinates: interpolated like on the fast path where the tile is smooth and
+    // interior (a footprint too wide for any box -- high source latitudes -- is usually still
+    // smooth), the exact chain elsewhere (source poles, source border, seam, EXACT).
+    const bool split = EQB_L2_SPLIT && (flags & L2_SPLIT) != 0;
+    int gx1 = gx0, gy1 = gy0;  // origin of the box of pixel slot 1
+    if (boxed) {
+      if (split) {
+        const int2 o = origin_r[k];
+        gx1 = o.x;
+        gy1 = o.y;
+      }
+      if (tid == 0) {
+        // the next tile's box is requested while this one is blended -- unless this tile
+        // holds both buffers: then after it (below)
+        if (split) {
+          issue_at(m, gx1, gy1, nbox + 1);
+        } else {
+          const int k2 = next_boxed(k);
+          if (k2 >= 0) issue(k2, nbox + 1);
+        }
+      }
+      __syncwarp();
+      mbar_wait_backoff(&full_bar[nbox & 1u], (nbox >> 1) & 1u);
+      if (split) mbar_wait_backoff(&full_bar[(nbox + 1u) & 1u], ((nbox + 1u) >> 1) & 1u);
+    }
+    {
+      const int pitch = boxed ? p.tma_bw[m] : 0;
+      const int bh = boxed ? p.tma_bh[m] : 0;
+      const T* const box0 = reinterpret_cast<const T*>(smem_raw + (nbox & 1u) * BUF);
+      const T* const box1 =
+          reinterpret_cast<const T*>(smem_raw + ((nbox + (split ? 1u : 0u)) & 1u) * BUF);
+      const bool interp = !EXACT && (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE)) == L2_SMOOTH;
+      float ixa[4], iya[4];
+      if (interp) {
+        const unsigned long long mone = pk2(-1.0f, -1.0f);
+#pragma unroll
+        for (int g = 0; g < 4 / P; ++g) {
+          const int r = row0 + 2 * ((g * P) >> 1);
+          const int iv = P == 1 ? (lx >> 3) + 2 * (g & 1) : (lx >> 2);
+          const unsigned long long* np =
+              reinterpret_cast<const unsigned long long*>(&nodes[r][k * 4 + iv]);
+          const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+          const unsigned long long d0n = fma2(n1, mone, n0), d2n = fma2(n1, mone, n2),
+                                   d3n = fma2(n1, mone, n3);
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const unsigned long long u =
+                fma2(wt[q][2], d3n, fma2(wt[q][1], d2n, fma2(wt[q][0], d0n, n1)));
+            unpk2(u, ixa[g * P + q], iya[g * P + q]);
+          }
+        }
+      } else {
+        RowCtx<XF> rc;
+#pragma unroll 1
+        for (int gy = 0; gy < 2; ++gy) {
+          const int yq = min(y0q + 2 * gy, p.dh - 1);
+          row_setup<XF>(p, b, yq, rc);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int x = min(tile_x0 + xloc(2 * gy + s), p.dw - 1);
+            float uj, ui;
+            coords<XF, false>(p, rc, b, x, yq, cell, x - cell * p.w_face, uj, ui);
+            ixa[2 * gy + s] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[2 * gy + s] = to_index(uj, p.inv_hm1, p.shm1f);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yq = y0q + 2 * (j >> 1), x = tile_x0 + xloc(j);
+        if (yq >= p.dh || x >= p.dw) continue;
+        const float ix = ixa[j], iy = iya[j];
+        const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
+        const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
+        const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
+        const float w_nw = __fmul_rn(ax, ay), w_ne = __fmul_rn(bx, ay);
+        const float w_sw = __fmul_rn(ax, by), w_se = __fmul_rn(bx, by);
+        const int xi = (int)xf, yi = (int)yf;
+        const int xr = xi - ((j & 1) ? gx1 : gx0), yr = yi - ((j & 1) ? gy1 : gy0);
+        const bool from_box = boxed && xr >= 0 && xr <= pitch - 2 && yr >= 0 && yr <= bh - 2;
+        const T* const box = (j & 1) ? box1 : box0;
+        T* d = ((j >> 1) ? d1 : d0) + (xloc(j) - lx * P);
+        float v[NC][4];
+        if (from_box) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const T* q0 = box + (c * bh + yr) * pitch + xr;
+            v[c][0] = lds_f(q0); v[c][1] = lds_f(q0 + 1);
+            v[c][2] = lds_f(q0 + pitch); v[c][3] = lds_f(q0 + pitch + 1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {  // (all loads of the pixel in flight together)
+            const T* q0 = src_b + (long long)c * p.ssc + (yi * ssh + xi);
+            if constexpr (ELT == 4) {
+              v[c][0] = ld_f(q0); v[c][1] = ld_f(q0 + 1);
+              v[c][2] = ld_f(q0 + ssh); v[c][3] = ld_f(q0 + ssh + 1);
+            } else {
+              ldg_pair<T>(q0, v[c][0], v[c][1]);
+              ldg_pair<T>(q0 + ssh, v[c][2], v[c][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const T o = OutCvt<T>::cvt(blend4(v[c][0], v[c][1], v[c][2], v[c][3], w_nw, w_ne, w_sw,
+                                            w_se), p.flags);
+          Pack<T, 1>::st(d + c * p.dsc, &o);
+        }
+      }
+    }
+    if (boxed) {
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty_bar[nbox & 1u]);
+        if (split) mbar_arrive(&empty_bar[(nbox + 1u) & 1u]);
+      }
+      if (split && tid == 0) {
+        const int k2 = next_boxed(k);
+        if (k2 >= 0) issue(k2, nbox + 2);
+      }
+      nbox += split ? 2u : 1u;
+    }
+  }
+}
+
+}  // namespace eqb
