@@ -54,7 +54,12 @@ constexpr int kL2MinBoxH = kL2TileH + 5;            // an upright tile: 16 rows 
 static_assert(kL2Boxes <= kTmaSlots, "tensor-map slots");
 
 // One box buffer (a CTA holds two).
-EQB_HD constexpr int l2_buf_bytes(int elt) { return elt == 4 ? 16 * 1024 : 12 * 1024; }
+#ifndef EQB_L2_BUF_KB_F32
+#define EQB_L2_BUF_KB_F32 18  // (measured 16 / 18 / 20 KB: 1.17 / 1.10 / 1.13 ms on 16 x 4K fp32, bench rotations)
+#endif
+EQB_HD constexpr int l2_buf_bytes(int elt) { return elt == 4 ? EQB_L2_BUF_KB_F32 * 1024 : 12 * 1024; }
+// CTAs per SM the shared memory allows (two buffers + ~6 KB of nodes, headers, reserve)
+EQB_HD constexpr int l2_ctas(int elt) { return 227 * 1024 / (2 * l2_buf_bytes(elt) + 6 * 1024); }
 
 // Box m: l2_box_w x l2_box_h source pixels x channels.  Boxes 0-1 are small (upright and
 // mildly rolled views); the others spend the whole buffer in different aspect ratios: 48
@@ -149,6 +154,34 @@ __device__ __forceinline__ void node_coords(const Params& p, const RowCtx<XF>& c
     rotate(c.A, mx, my, mz, X, Y, Z);
     spherical<false>(X, Y, Z, phi, theta);
     tail_minus_half<false>(phi, theta, p.shf, p.swf, uj, ui);
+  }
+}
+
+// Two nodes of one row at once (the packed chain, coords2).
+template <int XF>
+__device__ __forceinline__ void node_coords2(const Params& p, const RowCtx<XF>& c, int x0, int x1,
+                                             int cell, float (&ui)[2], float (&uj)[2]) {
+  if (XF == EQB_EQUI2EQUI) {
+    const int xa = x0 < 0 ? x0 + p.dw : (x0 >= p.dw ? x0 - p.dw : x0);
+    const int xb = x1 < 0 ? x1 + p.dw : (x1 >= p.dw ? x1 - p.dw : x1);
+    coords2<XF, false>(p, c, xa, xb, 0, 0.f, 0.f, ui, uj);
+  } else if (XF == EQB_EQUI2PERS) {
+    coords2<XF, false>(p, c, x0, x1, 0, 0.f, 0.f, ui, uj);
+  } else {  // EQB_EQUI2CUBE: the ramp continued linearly outside the face
+    const int w = p.w_face;
+    float rc[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int lx = (i ? x1 : x0) - cell * w;
+      if (lx >= 0 && lx < w) {
+        rc[i] = __ldg(p.tx + lx);
+      } else {
+        const float step = __ldg(p.tx + 1) - __ldg(p.tx);
+        rc[i] = lx < 0 ? fmaf((float)lx, step, __ldg(p.tx))
+                       : fmaf((float)(lx - (w - 1)), step, __ldg(p.tx + w - 1));
+      }
+    }
+    coords2<XF, false>(p, c, x0, x1, cell, rc[0], rc[1], ui, uj);
   }
 }
 
@@ -290,7 +323,7 @@ __device__ __forceinline__ void l2_blend(const L2Px (&q)[4], const float (&fx)[4
 }
 
 template <int XF, typename T, int NC, bool EXACT>
-__global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7)
+__global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 5 ? l2_ctas(4) : 5) : (EXACT ? 5 : 7))
     remap_lean2_kernel(const __grid_constant__ Params p) {
   constexpr int ELT = (int)sizeof(T);
   constexpr int PER16 = 16 / ELT;
@@ -324,10 +357,25 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7
     RowCtx<XF> rc;
     row_setup<XF>(p, b, y, rc);
     const int ncols = ntiles * 4 + 3;
-    for (int col = tid >> 4; col < ncols; col += kL2Warps * 32 / kL2TileH) {
-      float uj, ui;
-      node_coords<XF>(p, rc, strip_x0 + kL2Step * (col - 1), y, cell, uj, ui);
-      nodes[row][col] = make_float2(ui, uj);
+    constexpr int STEP = kL2Warps * 32 / kL2TileH;  // columns a thread advances by
+    if constexpr (EXACT) {
+      // two nodes per packed chain (coords2)
+      for (int col = tid >> 4; col < ncols; col += 2 * STEP) {
+        const int col2 = col + STEP < ncols ? col + STEP : col;
+        float ui[2], uj[2];
+        node_coords2<XF>(p, rc, strip_x0 + kL2Step * (col - 1), strip_x0 + kL2Step * (col2 - 1),
+                         cell, ui, uj);
+        nodes[row][col] = make_float2(ui[0], uj[0]);
+        nodes[row][col2] = make_float2(ui[1], uj[1]);
+      }
+    } else {
+      // (the packed chain is slower here: 1.41 vs 1.37 ms on the headline workload -- this
+      // variant runs at 72 registers for 7 CTAs per SM)
+      for (int col = tid >> 4; col < ncols; col += STEP) {
+        float uj, ui;
+        node_coords<XF>(p, rc, strip_x0 + kL2Step * (col - 1), y, cell, uj, ui);
+        nodes[row][col] = make_float2(ui, uj);
+      }
     }
   }
   __syncthreads();
@@ -494,14 +542,16 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7
         for (int gy = 0; gy < 2; ++gy) {
           const int y = min(y0q + 2 * gy, p.dh - 1);
           row_setup<XF>(p, b, y, rc);
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int j = 2 * gy + s, x = tile_x0 + xloc(j);
-            float uj, ui;
-            coords<XF, false>(p, rc, b, x, y, cell, x - cell * p.w_face, uj, ui);
-            ixa[j] = to_index(ui, p.inv_wm1, p.swm1f);
-            iya[j] = to_index(uj, p.inv_hm1, p.shm1f);
+          const int xa = tile_x0 + xloc(2 * gy), xb = tile_x0 + xloc(2 * gy + 1);
+          float rca = 0.f, rcb = 0.f;
+          if (XF == EQB_EQUI2CUBE) {
+            rca = __ldg(p.tx + (xa - cell * p.w_face));
+            rcb = __ldg(p.tx + (xb - cell * p.w_face));
           }
+          float i2[2], j2[2];
+          coords2<XF, true>(p, rc, xa, xb, cell, rca, rcb, i2, j2);
+          ixa[2 * gy] = i2[0]; ixa[2 * gy + 1] = i2[1];
+          iya[2 * gy] = j2[0]; iya[2 * gy + 1] = j2[1];
         }
       }
       L2Px px[4];
@@ -598,14 +648,17 @@ __global__ void __launch_bounds__(kL2Warps * 32, EXACT || sizeof(T) == 4 ? 5 : 7
         for (int gy = 0; gy < 2; ++gy) {
           const int yq = min(y0q + 2 * gy, p.dh - 1);
           row_setup<XF>(p, b, yq, rc);
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int x = min(tile_x0 + xloc(2 * gy + s), p.dw - 1);
-            float uj, ui;
-            coords<XF, false>(p, rc, b, x, yq, cell, x - cell * p.w_face, uj, ui);
-            ixa[2 * gy + s] = to_index(ui, p.inv_wm1, p.swm1f);
-            iya[2 * gy + s] = to_index(uj, p.inv_hm1, p.shm1f);
+          const int xa = min(tile_x0 + xloc(2 * gy), p.dw - 1);
+          const int xb = min(tile_x0 + xloc(2 * gy + 1), p.dw - 1);
+          float rca = 0.f, rcb = 0.f;
+          if (XF == EQB_EQUI2CUBE) {
+            rca = __ldg(p.tx + (xa - cell * p.w_face));
+            rcb = __ldg(p.tx + (xb - cell * p.w_face));
           }
+          float i2[2], j2[2];
+          coords2<XF, true>(p, rc, xa, xb, cell, rca, rcb, i2, j2);
+          ixa[2 * gy] = i2[0]; ixa[2 * gy + 1] = i2[1];
+          iya[2 * gy] = j2[0]; iya[2 * gy + 1] = j2[1];
         }
       }
 #pragma unroll

@@ -89,7 +89,7 @@ def compare(case, out, ref):
         d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
         d = np.minimum(d, 256 - d)
         assert np.mean(d <= 1) >= 0.9995  # (seam pixels, see close_except_seam)
-        assert rate(np.mean(d == 0), 0.99)
+        assert rate(np.mean(d == 0), 0.994)
     else:
         assert close_except_seam(out, ref, 5e-4, 0.9995)
         assert helpers.frac_close(out, ref, rtol=1e-5, atol=2e-5) >= 0.99
@@ -320,15 +320,15 @@ def test_low_precision_images_at_staged_sizes(dtype):
     o, r = out.float().cpu().numpy(), ref.float().numpy()
     d = np.abs(o - r)
     if dtype == torch.uint8:
-        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
+        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.994)
     else:
         ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
         assert close_except_seam(o, r, ulp * 1.01 + 2e-4, 0.99999)
-        assert rate(np.mean(d == 0), 0.97)
+        assert rate(np.mean(d == 0), 0.994)
     exact = equilib_b200.equi2equi(base.to(DEV), rots, fast_coords=False)
     same = float((exact == out).float().mean())
     print(f"{dtype}: fast == exact for {same:.5f} of outputs")
-    assert rate(same, 0.97)
+    assert rate(same, 0.994)
 
 
 # ---------------------------------------------------------------------------
@@ -402,7 +402,7 @@ def test_16bit_inputs(dtype, ulp, mode):
         assert rate(np.mean(o == r), 0.995)
     else:
         assert close_except_seam(o, r, ulp * 1.01 + 2e-4)
-        assert rate(np.mean(o == r), 0.98)
+        assert rate(np.mean(o == r), 0.997)
 
 
 @pytest.mark.parametrize("odd", [False, True])
@@ -690,7 +690,7 @@ def test_staged_channel_counts(channels):
     img = torch.from_numpy(cases.band_limited_image((2, channels, 512, 1024), "float32", px=96,
                                                     py=64)).to(torch.bfloat16)
     o, r = _oracle_vs_product("equi2equi", img, HARD_ROTS[1:3])
-    assert close_except_seam(o, r, 2.0 ** -7 * 1.01 + 2e-4, 0.99999) and rate(np.mean(o == r), 0.97)
+    assert close_except_seam(o, r, 2.0 ** -7 * 1.01 + 2e-4, 0.99999) and rate(np.mean(o == r), 0.997)
 
 
 def test_staged_expanded_batch_single_equirect_many_views():
@@ -711,7 +711,7 @@ def test_staged_expanded_batch_single_equirect_many_views():
     # view looking at the pole); everything else is within one fp16 ulp.
     tol = 2.0 ** -10 * 1.01 + 2e-4
     assert float((d <= tol).float().mean()) >= 0.99999
-    assert rate(float((d == 0).float().mean()), 0.97)
+    assert rate(float((d == 0).float().mean()), 0.99)
 
 
 def test_staged_sizes_not_multiples_of_the_tile():
@@ -724,10 +724,10 @@ def test_staged_sizes_not_multiples_of_the_tile():
         out = equilib_b200.equi2equi(x.to(DEV), rots, height=503, width=1012)
         ref = oracle.equi2equi(x, rots, height=503, width=1012, flavour="cuda")
         d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
+        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.995)
         exact = equilib_b200.equi2equi(x.to(DEV), rots, height=503, width=1012, fast_coords=False)
         d2 = np.abs(exact.cpu().numpy().astype(int) - ref.numpy().astype(int))
-        assert np.mean(d2 <= 1) >= 0.9999 and rate(np.mean(d2 == 0), 0.99)
+        assert np.mean(d2 <= 1) >= 0.9999 and rate(np.mean(d2 == 0), 0.997)
 
 
 def test_staged_8k_source_bicubic_uint8():
@@ -750,7 +750,7 @@ def test_equi2cube_fast_coordinates_faces_of_64():
         out = equilib_b200.equi2cube(img.to(DEV), rots, w_face, "dice")
         ref = oracle.equi2cube(img, rots, w_face, "dice", flavour="cuda")
         d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
+        assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.997)
 
 
 # --- channels-last uint8 -------------------------------------------------
@@ -779,7 +779,7 @@ def test_channels_last_uint8_in_place(transform, channels):
     assert int(d.max()) <= 1 and rate(float((d == 0).float().mean()), 0.999)
     ref = getattr(oracle, transform)(img, rots, *args, flavour="cuda")
     d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-    assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.97)
+    assert np.mean(d <= 1) >= 0.9999 and rate(np.mean(d == 0), 0.996)
 
 
 def test_channels_last_ragged_and_pole_tiles():
@@ -792,7 +792,7 @@ def test_channels_last_ragged_and_pole_tiles():
     assert out.is_contiguous(memory_format=torch.channels_last)
     ref = oracle.equi2equi(img, rots, height=516, width=1036, flavour="cuda")
     d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
-    assert np.mean(d <= 1) >= 0.9995 and rate(np.mean(d == 0), 0.97)
+    assert np.mean(d <= 1) >= 0.9995 and rate(np.mean(d == 0), 0.995)
 
 
 def test_channels_last_falls_back_to_planar_where_not_served():
@@ -839,7 +839,7 @@ def test_lean_kernel_random_rotations_match_the_exact_path():
         # one bf16 ulp of values in [0, 1] is 2^-8 at most; seam pixels may flip (see
         # close_except_seam)
         assert float((d <= 2.0 ** -8 * 1.01).float().mean()) >= 0.9999
-        assert rate(float((d == 0).float().mean()), 0.995)
+        assert rate(float((d == 0).float().mean()), 0.9975)
         u8 = (img.float() * 255).to(torch.uint8)
         a = equilib_b200.equi2equi(u8, rots).int()
         b = equilib_b200.equi2equi(u8, rots, fast_coords=False).int()
