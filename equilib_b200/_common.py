@@ -3,6 +3,7 @@ and the call into the ``equilib_b200::remap`` op."""
 
 from __future__ import annotations
 
+import functools
 import os
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -92,11 +93,56 @@ def check_image(img: torch.Tensor, name: str, allow_channels_last: bool = False)
         f"ERR: input {name} has dtype of {img.dtype} which is\n"
         f"incompatible: try {SUPPORTED}"
     )
-    if img.dtype == torch.float64:
-        raise NotImplementedError("float64 images are not implemented by equilib_b200")
+    if img.dtype == torch.float64:  # (the public functions convert first: accepts_float64)
+        raise NotImplementedError("float64 images reach the kernels as float32 (accepts_float64)")
     if img.stride(3) != 1 and not (allow_channels_last and is_channels_last_u8(img)):
         img = img.contiguous()
     return img
+
+
+_IMAGE_ARGS = ("src", "equi", "cubemap", "pers")
+
+
+def _cast_tree(x, src_dtype, dst_dtype):
+    if torch.is_tensor(x):
+        return x.to(dst_dtype) if x.dtype == src_dtype else x
+    if isinstance(x, list):
+        return [_cast_tree(v, src_dtype, dst_dtype) for v in x]
+    if isinstance(x, dict):
+        return {k: _cast_tree(v, src_dtype, dst_dtype) for k, v in x.items()}
+    return x
+
+
+def _has_dtype(x, dtype) -> bool:
+    if torch.is_tensor(x):
+        return x.dtype == dtype
+    if isinstance(x, list):
+        return any(_has_dtype(v, dtype) for v in x)
+    if isinstance(x, dict):
+        return any(_has_dtype(v, dtype) for v in x.values())
+    return False
+
+
+def accepts_float64(fn):
+    """float64 images (which the reference accepts, e.g. equilib/equi2equi/torch.py:87-95, and
+    processes in float64) are computed in float32 and returned as float64: the kernels'
+    arithmetic is the reference's float32 chain, so the result agrees with the reference's
+    float64 result to float32 accuracy (~1e-6 relative on band-limited images), not bit for
+    bit.  Documented deviation; every other dtype keeps its own policy."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        first = args[0] if args else next((kwargs[k] for k in _IMAGE_ARGS if k in kwargs), None)
+        if not _has_dtype(first, torch.float64):
+            return fn(*args, **kwargs)
+        if args:
+            args = (_cast_tree(args[0], torch.float64, torch.float32),) + tuple(args[1:])
+        else:
+            kwargs = {k: (_cast_tree(v, torch.float64, torch.float32) if k in _IMAGE_ARGS else v)
+                      for k, v in kwargs.items()}
+        return _cast_tree(fn(*args, **kwargs), torch.float32, torch.float64)
+
+    return wrapper
 
 
 def is_channels_last_u8(img: torch.Tensor) -> bool:

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "remap_kernels.cuh"
 #include "remap_lean2.cuh"
@@ -214,14 +215,69 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
+// ---- tensor-map cache ---------------------------------------------------------------------
+// Encoding a tensor map costs ~1 us and a staged launch needs up to 13 of them; repeated
+// launches on the same source (video frames in a reused buffer, BASELINE config 1's 6 us kernel)
+// would spend more host time encoding than the kernel runs.  A tensor map is a pure function of
+// (data type, base pointer, dims, strides, box), so encoded maps are kept in a small direct-
+// mapped table keyed by exactly those values.  (All maps here: rank 4, element strides 1, no
+// interleave / swizzle, 128-byte L2 promotion, zero fill.)
+struct TmapKey {
+  unsigned long long ptr, dims[4], strides[3];
+  unsigned box[4];
+  int dt;
+  bool operator==(const TmapKey& o) const { return std::memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  TmapKey key;
+  CUtensorMap map;
+  bool used;
+};
+static std::mutex g_tmap_mutex;
+static TmapSlot g_tmap_cache[512];
+
+static CUresult encode_cached(CUtensorMap* out, CUtensorMapDataType dt, void* ptr,
+                              const cuuint64_t* dims, const cuuint64_t* strides,
+                              const cuuint32_t* box) {
+  TmapKey k;
+  std::memset(&k, 0, sizeof(k));
+  k.ptr = reinterpret_cast<unsigned long long>(ptr);
+  for (int i = 0; i < 4; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i < 3; ++i) k.strides[i] = strides[i];
+  k.dt = (int)dt;
+  unsigned long long h = 1469598103934665603ull;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+  for (size_t i = 0; i < sizeof(k); ++i) h = (h ^ b[i]) * 1099511628211ull;
+  TmapSlot& slot = g_tmap_cache[h % 512];
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (slot.used && slot.key == k) {
+      *out = slot.map;
+      return CUDA_SUCCESS;
+    }
+  }
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return CUDA_ERROR_NOT_SUPPORTED;
+  const cuuint32_t ones[4] = {1, 1, 1, 1};
+  const CUresult r = enc(out, dt, 4, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    slot.key = k;
+    slot.map = *out;
+    slot.used = true;
+  }
+  return r;
+}
+
 // Tensor maps over the source viewed as (W, H, C, B): a wide box for near-upright views,
 // a square one for views rotated by 45 degrees and one in between, all within the
 // kernel's shared-memory budget.
 static void setup_tma(const eqb_remap_desc* d, Params& p, bool lean) {
   p.use_tma = 0;
   if (d->flags & EQB_FLAG_NO_TMA) return;
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return;
+  if (!encode_tiled()) return;
   const int elt = (int)elt_size(d->dtype);
   // box shapes: the compile-time table the kernels are specialised on
   int bw[kTmaBoxes], bh[kTmaBoxes];
@@ -244,12 +300,10 @@ static void setup_tma(const eqb_remap_desc* d, Params& p, bool lean) {
                                          : (d->channels > 1 ? cstride : (cuuint64_t)d->src_stride_h * elt * d->src_h) * d->channels};
   for (int i = 0; i < 3; ++i)
     if (strides[i] == 0 || strides[i] % 16) return;
-  const cuuint32_t ones[4] = {1, 1, 1, 1};
   for (int m = 0; m < kTmaBoxes; ++m) {
     const cuuint32_t box[4] = {(cuuint32_t)bw[m], (cuuint32_t)bh[m], (cuuint32_t)d->channels, 1};
-    if (enc(&p.tmaps[m], dt, 4, const_cast<void*>(d->src), dims, strides, box, ones,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (encode_cached(&p.tmaps[m], dt, const_cast<void*>(d->src), dims, strides, box) !=
+        CUDA_SUCCESS)
       return;
     p.tma_bw[m] = bw[m];
     p.tma_bh[m] = bh[m];
@@ -306,8 +360,7 @@ static bool can_nhwc(const eqb_remap_desc* d) {
 // Tensor maps for the channels-last kernel: a source row is W*C/4 32-bit words.
 static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
   p.use_tma = 0;
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return;
+  if (!encode_tiled()) return;
   const int c = d->channels;
   const bool batched = d->src_stride_b > 0 && d->batch > 1;
   const cuuint64_t row = (cuuint64_t)d->src_stride_h;  // bytes (uint8)
@@ -315,15 +368,13 @@ static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
                               (cuuint64_t)(batched ? d->batch : 1)};
   const cuuint64_t strides[3] = {row, row * d->src_h,
                                  batched ? (cuuint64_t)d->src_stride_b : row * d->src_h};
-  const cuuint32_t ones[4] = {1, 1, 1, 1};
   for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
   for (int m = 0; m < kTmaBoxes; ++m) {
     const int bw = box_w(1, m), bh = lean_box_h(1, m, c);
     if (bw * c / 4 > 256) continue;  // (box dimensions are limited to 256 elements)
     const cuuint32_t box[4] = {(cuuint32_t)(bw * c / 4), (cuuint32_t)bh, 1, 1};
-    if (enc(&p.tmaps[m], CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(d->src), dims,
-            strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (encode_cached(&p.tmaps[m], CU_TENSOR_MAP_DATA_TYPE_UINT32, const_cast<void*>(d->src),
+                      dims, strides, box) != CUDA_SUCCESS)
       return;
     p.tma_bw[m] = bw;
     p.tma_bh[m] = bh;
@@ -365,8 +416,7 @@ static bool can_lean2(const eqb_remap_desc* d) {
 
 static void setup_tma_l2(const eqb_remap_desc* d, Params& p) {
   p.use_tma = 0;
-  EncodeTiledFn enc = encode_tiled();
-  if (!enc) return;
+  if (!encode_tiled()) return;
   const int elt = (int)elt_size(d->dtype);
   CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                            : d->dtype == EQB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -382,15 +432,13 @@ static void setup_tma_l2(const eqb_remap_desc* d, Params& p) {
                                          : cstride * d->channels};
   for (int i = 0; i < 3; ++i)
     if (strides[i] == 0 || strides[i] % 16) return;
-  const cuuint32_t ones[4] = {1, 1, 1, 1};
   for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
   for (int m = 0; m < kL2Boxes; ++m) {
     const int bw = l2_box_w(elt, m), bh = l2_box_h(elt, d->channels, m);
     if (bw > 256 || bh < kL2MinBoxH) continue;
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)d->channels, 1};
-    if (enc(&p.tmaps[m], dt, 4, const_cast<void*>(d->src), dims, strides, box, ones,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    if (encode_cached(&p.tmaps[m], dt, const_cast<void*>(d->src), dims, strides, box) !=
+        CUDA_SUCCESS)
       return;
     p.tma_bw[m] = bw;
     p.tma_bh[m] = bh;

@@ -85,6 +85,7 @@ def _face_lists(cubemap, cube_format: str) -> List[List[torch.Tensor]]:
     return [[cube[k] for k in FACE_KEYS] for cube in cubemap]
 
 
+@K.accepts_float64
 def cube2equi(
     cubemap,
     cube_format: str,

@@ -62,6 +62,7 @@ class Equi2Cube(object):
         )
 
 
+@K.accepts_float64
 def equi2cube(
     equi: torch.Tensor,
     rots: Rot,

@@ -48,6 +48,7 @@ class Equi2Equi(object):
         )
 
 
+@K.accepts_float64
 def equi2equi(
     src: torch.Tensor,
     rots: Rot,

@@ -69,6 +69,7 @@ class Equi2Pers(object):
         )
 
 
+@K.accepts_float64
 def equi2pers(
     equi: torch.Tensor,
     rots: Rot,

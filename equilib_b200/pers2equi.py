@@ -49,6 +49,7 @@ class Pers2Equi(object):
         )
 
 
+@K.accepts_float64
 def pers2equi(
     pers: torch.Tensor,
     rots: Rot,

@@ -70,7 +70,25 @@ def main():
     torch.cuda.synchronize()
     report("1: same, wall clock per call incl. python + custom-op dispatch",
            (time.perf_counter() - t0) / 200 * 1e3, 480 * 640, 480 * 640 * 3 * 4 * 2)
-    del equi
+    # the same call captured in a CUDA graph and replayed (no python on the replay path)
+    e4 = equi.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        op(e4, [rot])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        op(e4, [rot])
+    g.replay()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(500):
+        g.replay()
+    torch.cuda.synchronize()
+    report("1: same, one CUDA-graph replay per call (wall clock)",
+           (time.perf_counter() - t0) / 500 * 1e3, 480 * 640, 480 * 640 * 3 * 4 * 2)
+    del equi, e4, g
 
     # config 2 family: equi2equi batch 32 bf16 / fp32 / uint8, three modes
     for dtype, b in ((torch.bfloat16, 32), (torch.float32, 16), (torch.uint8, 32)):
