@@ -31,6 +31,7 @@ FLAG_NO_LEAN = 1024
 FLAG_CHANNELS_LAST = 2048
 FLAG_NO_LEAN2 = 4096
 FLAG_FORCE_LEAN2 = 8192
+FLAG_COMPACT_MAP = 32768
 MAP_TILE_W, MAP_TILE_H = 64, 8
 FLAG_WARP_SHAPE_SHIFT = 8
 

@@ -207,10 +207,10 @@ def coords(coords_out: Tensor, mats, tab_x, tab_y, itab_x, grid, transform: int,
 
 def map_build(coords_t: Tensor, map_t: Tensor, heads_t: Tensor, dtype: torch.dtype, channels: int,
               mats, tab_x, tab_y, itab_x, transform: int, batch: int, src_h: int, src_w: int,
-              dst_h: int, dst_w: int) -> None:
+              dst_h: int, dst_w: int, flags: int = 0) -> None:
     """eqb_map_build: pack the coordinates of a fixed set of rotations into a sampling map."""
     _require_cuda(coords_t, "coords")
-    d = _fill_desc(None, None, mats, tab_x, tab_y, itab_x, None, None, transform, 1, 0, batch,
+    d = _fill_desc(None, None, mats, tab_x, tab_y, itab_x, None, None, transform, 1, flags, batch,
                    channels, src_h, src_w, dst_h, dst_w, (0, 0, 0), (0, 0, 0), 0, 0, 0,
                    [0] * 12, None)
     d.dtype = dtype_code(dtype)

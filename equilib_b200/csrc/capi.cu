@@ -73,6 +73,7 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
   p.swm1f = (float)(d->src_w - 1);
   p.inv_wface = d->w_face > 0 ? 1.0f / (float)d->w_face : 0.0f;
   p.one = 1.0f;
+  p.xf = d->transform;
   p.iters = 1;
   p.w_face = d->w_face;
   p.n_cells = d->n_cells;

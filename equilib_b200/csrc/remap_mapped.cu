@@ -19,9 +19,15 @@ constexpr unsigned kFracOne = 65535u;  // fractions are stored as round(f * 6553
 // One CTA per 64 x 8 tile, lanes laid out as in the lean kernel (16 x 2 lanes per warp, a
 // lane owns 4 consecutive pixels).  Coordinates go through the same to_index / floor /
 // footprint shift as the remap kernels, so the taps are the ones the exact path uses.
+// COMPACT: 4 bytes per pixel -- the tap as an offset from the tile's box origin (x: 8 bits,
+// y: 8 bits; boxes are at most 256 x 128) and the two fractions as round(f * 255) -- written
+// after the tile's box is known.  Tiles without a box store nothing usable: the remap
+// kernel evaluates the exact chain for them (source poles, the seam: a few per cent).
+template <bool COMPACT>
 __global__ void __launch_bounds__(kLeanWarps * 32)
     map_pack_kernel(const __grid_constant__ Params p, const float* __restrict__ coords,
-                    uint2* __restrict__ map, int4* __restrict__ heads, int per16) {
+                    void* __restrict__ map_out, int4* __restrict__ heads, int per16) {
+  uint2* const map = static_cast<uint2*>(map_out);
   __shared__ int bbox[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lx = lane % kStLaneW, ly = lane / kStLaneW;
@@ -31,6 +37,8 @@ __global__ void __launch_bounds__(kLeanWarps * 32)
   if (tid == 0) { bbox[0] = 0x7fffffff; bbox[1] = 0x7fffffff; bbox[2] = -1; bbox[3] = -1; }
   __syncthreads();
   int nx = 0x7fffffff, ny = 0x7fffffff, mx = -1, my = -1;
+  int cxi[4] = {0, 0, 0, 0}, cyi[4] = {0, 0, 0, 0};
+  unsigned cq[4] = {0, 0, 0, 0};
   if (yq < p.dh) {
     const long long plane = (long long)p.dh * p.dw;
     const float* cj = coords + (long long)b * 2 * plane + (long long)yq * p.dw;
@@ -44,9 +52,14 @@ __global__ void __launch_bounds__(kLeanWarps * 32)
       const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
       const float fx = __fsub_rn(ix, xf), fy = __fsub_rn(iy, yf);
       const int xi = (int)xf, yi = (int)yf;
-      const unsigned qx = (unsigned)__float2int_rn(fx * (float)kFracOne);
-      const unsigned qy = (unsigned)__float2int_rn(fy * (float)kFracOne);
-      mrow[x] = make_uint2((unsigned)xi | ((unsigned)yi << 16), qx | (qy << 16));
+      if (COMPACT) {
+        cxi[i] = xi; cyi[i] = yi;
+        cq[i] = (unsigned)__float2int_rn(fx * 255.0f) | ((unsigned)__float2int_rn(fy * 255.0f) << 8);
+      } else {
+        const unsigned qx = (unsigned)__float2int_rn(fx * (float)kFracOne);
+        const unsigned qy = (unsigned)__float2int_rn(fy * (float)kFracOne);
+        mrow[x] = make_uint2((unsigned)xi | ((unsigned)yi << 16), qx | (qy << 16));
+      }
       nx = min(nx, xi); ny = min(ny, yi); mx = max(mx, xi); my = max(my, yi);
     }
   }
@@ -70,16 +83,29 @@ __global__ void __launch_bounds__(kLeanWarps * 32)
     const long long tile =
         ((long long)b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     heads[tile] = make_int4(gx0, gy0, m, 0);
+    bbox[0] = gx0;
+    bbox[1] = gy0;
+    bbox[2] = m;
+  }
+  if (COMPACT) {
+    __syncthreads();
+    if (yq < p.dh && bbox[2] >= 0) {
+      unsigned* crow = static_cast<unsigned*>(map_out) + ((long long)b * p.dh + yq) * p.dw;
+      for (int i = 0; i < 4 && x0 + i < p.dw; ++i)
+        crow[x0 + i] = (unsigned)(cxi[i] - bbox[0]) | ((unsigned)(cyi[i] - bbox[1]) << 8) |
+                       (cq[i] << 16);
+    }
   }
 }
 
 // ---- remap from the map ------------------------------------------------------------------
 // IL = 0: NC planar channels.  IL = 3 / 4: channels-last uint8 RGB / RGBX (NC == IL), the
 // layout of decoded video frames, read and written in place (see nhwc_blend).
-template <typename T, int NC, int IL = 0>
+template <typename T, int NC, int IL = 0, bool CM = false>
 __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
-    remap_mapped_kernel(const __grid_constant__ Params p, const uint2* __restrict__ map,
+    remap_mapped_kernel(const __grid_constant__ Params p, const void* __restrict__ map_in,
                         const int4* __restrict__ heads, int tiles_x) {
+  const uint2* const map = static_cast<const uint2*>(map_in);
   constexpr int PX = 4;
   constexpr int ELT = (int)sizeof(T);
   constexpr int PXE = IL ? IL : 1;  // elements from a pixel to its right neighbour
@@ -98,6 +124,8 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
   const T* const src_b = static_cast<const T*>(p.src) + (long long)b * p.ssb;
   T* const dst_row = static_cast<T*>(p.dst) + (long long)b * p.dsb + (long long)y * p.dsh;
   const uint2* const map_row = map + ((long long)b * p.dh + y) * p.dw;
+  const unsigned* const cmap_row =
+      static_cast<const unsigned*>(map_in) + ((long long)b * p.dh + y) * p.dw;
   const int4* const head_row = heads + ((long long)b * gridDim.y + blockIdx.y) * tiles_x;
   const int ssh = (int)p.ssh;
   const float q = 1.0f / (float)kFracOne;
@@ -120,7 +148,46 @@ __global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
     }
     unsigned a[PX];
     float fx[PX], fy[PX];
-    {
+    if constexpr (CM) {
+      if (boxed) {
+        unsigned e[PX];
+        if (live && x0 + PX <= p.dw) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(cmap_row + x0));
+          e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < PX; ++i) e[i] = __ldg(cmap_row + min(x0 + i, p.dw - 1));
+        }
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+          const int xr = (int)(e[i] & 0xffu), yr = (int)((e[i] >> 8) & 0xffu);
+          fx[i] = (float)((e[i] >> 16) & 0xffu) * (1.0f / 255.0f);
+          fy[i] = (float)(e[i] >> 24) * (1.0f / 255.0f);
+          a[i] = tile_s + (unsigned)((yr * pitch + xr) * (PXE * ELT));
+        }
+      } else {
+        // no box, no map entry: the exact chain (source poles, the seam)
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+          const int x = min(x0 + i, p.dw - 1);
+          float uj, ui;
+          if (p.xf == EQB_EQUI2EQUI) {
+            RowCtx<EQB_EQUI2EQUI> rc;
+            row_setup<EQB_EQUI2EQUI>(p, b, y, rc);
+            coords<EQB_EQUI2EQUI, false>(p, rc, b, x, y, 0, 0, uj, ui);
+          } else {
+            RowCtx<EQB_EQUI2PERS> rc;
+            row_setup<EQB_EQUI2PERS>(p, b, y, rc);
+            coords<EQB_EQUI2PERS, false>(p, rc, b, x, y, 0, 0, uj, ui);
+          }
+          const float ix = to_index(ui, p.inv_wm1, p.swm1f), iy = to_index(uj, p.inv_hm1, p.shm1f);
+          const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
+          fx[i] = __fsub_rn(ix, xf);
+          fy[i] = __fsub_rn(iy, yf);
+          a[i] = (unsigned)((int)yf * ssh + (int)xf * PXE);
+        }
+      }
+    } else {
       uint2 e[PX];
       if (live && x0 + PX <= p.dw) {
         const uint4 e01 = __ldg(reinterpret_cast<const uint4*>(map_row + x0));
@@ -222,8 +289,12 @@ cudaError_t launch_map_pack(const Params& p, const float* coords, void* map, voi
                             int elt, cudaStream_t stream) {
   const dim3 grid((unsigned)((p.dw + 63) / 64), (unsigned)((p.dh + kLeanTileH - 1) / kLeanTileH),
                   (unsigned)p.B);
-  map_pack_kernel<<<grid, kLeanWarps * 32, 0, stream>>>(
-      p, coords, static_cast<uint2*>(map), static_cast<int4*>(heads), 16 / elt);
+  if (p.flags & EQB_FLAG_COMPACT_MAP)
+    map_pack_kernel<true><<<grid, kLeanWarps * 32, 0, stream>>>(p, coords, map,
+                                                                static_cast<int4*>(heads), 16 / elt);
+  else
+    map_pack_kernel<false><<<grid, kLeanWarps * 32, 0, stream>>>(
+        p, coords, map, static_cast<int4*>(heads), 16 / elt);
   return cudaGetLastError();
 }
 
@@ -237,8 +308,12 @@ static cudaError_t launch_mapped_nc(Params p, const void* map, const void* heads
   p.iters = tiles >= wave * 8 * 16 ? 16 : tiles >= wave * 16 ? 4 : 1;
   const dim3 grid((unsigned)((tiles_x + p.iters - 1) / p.iters), (unsigned)tiles_y, (unsigned)p.B);
   // (+16: the channels-last RGB tap loads are aligned words that may end past the last tap)
-  remap_mapped_kernel<T, NC, IL><<<grid, kLeanWarps * 32, lean_smem_bytes() + 16, stream>>>(
-      p, static_cast<const uint2*>(map), static_cast<const int4*>(heads), tiles_x);
+  if (p.flags & EQB_FLAG_COMPACT_MAP)
+    remap_mapped_kernel<T, NC, IL, true><<<grid, kLeanWarps * 32, lean_smem_bytes() + 16, stream>>>(
+        p, map, static_cast<const int4*>(heads), tiles_x);
+  else
+    remap_mapped_kernel<T, NC, IL, false><<<grid, kLeanWarps * 32, lean_smem_bytes() + 16, stream>>>(
+        p, map, static_cast<const int4*>(heads), tiles_x);
   return cudaGetLastError();
 }
 

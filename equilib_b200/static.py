@@ -4,8 +4,9 @@ For video from a fixed rig the rotations of every call are the same; the referen
 recomputes rotation, spherical mapping and normalisation per call anyway (its grid cache,
 equilib/_cache.py:21-40, keeps only the rays) and lists "full-grid cache for the
 fixed-rotation case" as future work (README.md:168).  ``StaticRemap`` is that cache for
-the CUDA path: 8 bytes per output pixel (top-left tap and the two bilinear fractions)
-plus the shared-memory box of every output tile.  Applying it runs none of the coordinate
+the CUDA path: 8 bytes per output pixel (top-left tap and the two bilinear fractions) -- or 4
+with ``compact=True`` (tap relative to the tile's box, 8-bit fractions) -- plus the
+shared-memory box of every output tile.  Applying it runs none of the coordinate
 chain -- the kernel reads the map, loads the box with TMA and blends.
 
     sr = StaticRemap.equi2equi(rots, src_shape=frames.shape, dtype=frames.dtype,
@@ -31,7 +32,8 @@ __all__ = ["StaticRemap"]
 
 class StaticRemap:
     def __init__(self, transform: int, mats, tab_x, tab_y, src_shape: Tuple[int, int, int, int],
-                 dst_hw: Tuple[int, int], dtype: torch.dtype, device: torch.device) -> None:
+                 dst_hw: Tuple[int, int], dtype: torch.dtype, device: torch.device,
+                 compact: bool = False) -> None:
         b, c, sh, sw = (int(v) for v in src_shape)
         dh, dw = int(dst_hw[0]), int(dst_hw[1])
         if dtype not in (torch.uint8, torch.float16, torch.bfloat16):
@@ -47,15 +49,21 @@ class StaticRemap:
         _ops.coords(coords, mats, tab_x, tab_y, None, None, transform, b, sh, sw, dh, dw)
         ty = (dh + _lib.MAP_TILE_H - 1) // _lib.MAP_TILE_H
         tx = (dw + _lib.MAP_TILE_W - 1) // _lib.MAP_TILE_W
-        self.map = torch.empty((b, dh, dw, 2), dtype=torch.int32, device=device)
+        # 8 bytes per pixel (absolute tap, 16-bit fractions) or, compact, 4 (tap relative to the
+        # tile's box, 8-bit fractions: coordinates to 1/510 pixel; tiles that fit no box have
+        # no entries -- the kernel runs the exact chain there)
+        self.compact = bool(compact)
+        self._map_flags = _lib.FLAG_COMPACT_MAP if self.compact else 0
+        self.map = torch.empty((b, dh, dw) if self.compact else (b, dh, dw, 2),
+                               dtype=torch.int32, device=device)
         self.heads = torch.empty((b, ty, tx, 4), dtype=torch.int32, device=device)
         _ops.map_build(coords, self.map, self.heads, dtype, c, mats, tab_x, tab_y, None,
-                       transform, b, sh, sw, dh, dw)
+                       transform, b, sh, sw, dh, dw, flags=self._map_flags)
 
     @classmethod
     def equi2equi(cls, rots: Sequence[Dict[str, float]], src_shape, dtype, device,
                   height: Optional[int] = None, width: Optional[int] = None,
-                  z_down: bool = False) -> "StaticRemap":
+                  z_down: bool = False, compact: bool = False) -> "StaticRemap":
         """The map of ``equi2equi(src, rots, height=, width=, z_down=)``."""
         rots = _as_list(rots, src_shape)
         device = _device(device)
@@ -63,18 +71,20 @@ class StaticRemap:
         dw = int(width) if width is not None else int(src_shape[3])
         mats = _prep.mats_for("rot", rots, z_down, device)
         tab_x, tab_y = _prep.equirect_tables(dh, dw, device)
-        return cls(_lib.EQUI2EQUI, mats, tab_x, tab_y, src_shape, (dh, dw), dtype, device)
+        return cls(_lib.EQUI2EQUI, mats, tab_x, tab_y, src_shape, (dh, dw), dtype, device,
+                   compact=compact)
 
     @classmethod
     def equi2pers(cls, rots: Sequence[Dict[str, float]], src_shape, dtype, device, height: int,
                   width: int, fov_x: float, skew: float = 0.0,
-                  z_down: bool = False) -> "StaticRemap":
+                  z_down: bool = False, compact: bool = False) -> "StaticRemap":
         """The map of ``equi2pers(equi, rots, height, width, fov_x, skew=, z_down=)``."""
         rots = _as_list(rots, src_shape)
         device = _device(device)
         mats = _prep.mats_for("equi2pers", rots, z_down, device,
                               (int(height), int(width), float(fov_x), float(skew)))
-        return cls(_lib.EQUI2PERS, mats, None, None, src_shape, (height, width), dtype, device)
+        return cls(_lib.EQUI2PERS, mats, None, None, src_shape, (height, width), dtype, device,
+                   compact=compact)
 
     def __call__(self, src: torch.Tensor, out: Optional[torch.Tensor] = None,
                  saturate_uint8: bool = False) -> torch.Tensor:
@@ -86,6 +96,7 @@ class StaticRemap:
                 f"{tuple(src.shape)} {src.dtype} on {src.device}")
         b, c = self.src_shape[:2]
         flags = _lib.FLAG_SATURATE_U8 if (saturate_uint8 and src.dtype == torch.uint8) else 0
+        flags |= self._map_flags
         # uint8 RGB / RGBX frames in torch.channels_last (the decoder's layout) are read and
         # written in place, like in equi2equi / equi2pers
         cl = src.stride(3) != 1 and K.is_channels_last_u8(src) and src.stride(2) % 16 == 0 \

@@ -77,6 +77,8 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
                                      variant would run                                     */
 #define EQB_FLAG_NO_LEAN2 4096u   /* experiments: the round-1 lean kernel where the strip-node \
                                      kernel (remap_lean2.cuh) would run                    */
+#define EQB_FLAG_COMPACT_MAP 32768u /* eqb_map_build / eqb_remap_mapped: 4-byte map entries   \
+                                      (see eqb_map_build)                                    */
 #define EQB_FLAG_FORCE_LEAN2 8192u /* experiments: strip-node kernel for uint8 too          */
 #define EQB_FLAG_CHANNELS_LAST 2048u /* src and dst are channels-last (NHWC): channel stride  \
                                        1, pixel stride = channels; strides_h in elements.     \
@@ -183,6 +185,11 @@ int32_t eqb_remap_supports_channels_last(const eqb_remap_desc* desc);
  * (batch x ceil(dst_h / TILE_H) x ceil(dst_w / TILE_W) entries: origin and shape index of
  * the shared-memory box the tile's footprint fits, or -1).  desc->dtype and
  * desc->channels select the box table; src / dst are not touched.
+ * With EQB_FLAG_COMPACT_MAP the entries are 4 bytes (the reference roadmap's "compact"
+ * full-grid cache, README.md:168): the tap as an offset from the tile's box origin (x | y << 8)
+ * and the fractions as round(f * 255) << 16 / << 24 -- coordinates quantised to 1/510 pixel;
+ * tiles without a box have no entries and eqb_remap_mapped evaluates the exact chain for them
+ * (mats / tables of the descriptor must then be those the map was built from).
  *
  * eqb_remap_mapped remaps desc->src into desc->dst from such a map: bilinear, planar
  * 1 / 3 / 4 channels of uint8 / fp16 / bf16 -- or, with EQB_FLAG_CHANNELS_LAST, uint8 RGB /

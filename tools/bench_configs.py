@@ -162,8 +162,18 @@ def main():
         torch.cuda.synchronize()
         build_ms = (time.perf_counter() - t0) * 1e3
         ms = timed(lambda: sr(src))
+        alg = 2 * px * 3 * src.element_size()  # source + output, the map is overhead
         report(f"N3: equi2equi {str(dtype)[6:]} b32 4K bilinear through a static map", ms, px,
-               2 * px * 3 * src.element_size() + 8 * px, map_build_ms=round(build_ms, 2))
+               alg + 8 * px, map_build_ms=round(build_ms, 2),
+               frac_hbm_on_8d_bytes=round(alg / ms / 1e6 / 6553.3, 4),
+               note="alg_gb_s / frac_hbm_6553 count the 8 B/px map read too")
+        sr4 = equilib_b200.StaticRemap.equi2equi(r, src.shape, dtype, DEV, compact=True)
+        ms4 = timed(lambda: sr4(src))
+        report(f"N3: equi2equi {str(dtype)[6:]} b32 4K bilinear through a COMPACT static map "
+               "(4 B/px)", ms4, px, alg + 4 * px,
+               frac_hbm_on_8d_bytes=round(alg / ms4 / 1e6 / 6553.3, 4),
+               note="alg_gb_s / frac_hbm_6553 count the 4 B/px map read too")
+        del sr4
         if dtype == torch.uint8:
             src_cl = src.contiguous(memory_format=torch.channels_last)
             ms = timed(lambda: sr(src_cl))
