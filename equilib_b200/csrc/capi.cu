@@ -73,6 +73,7 @@ static int fill(const eqb_remap_desc* d, bool need_images, Params& p) {
   p.swm1f = (float)(d->src_w - 1);
   p.inv_wface = d->w_face > 0 ? 1.0f / (float)d->w_face : 0.0f;
   p.one = 1.0f;
+  p.face_maps = 0;
   p.xf = d->transform;
   p.iters = 1;
   p.w_face = d->w_face;
@@ -172,14 +173,26 @@ static bool dst_vector_ok(const eqb_remap_desc* d, int v) {
   return true;
 }
 
+static bool tma_available();  // (cuTensorMapEncodeTiled resolved, below)
+
+static bool cube_is_horizon(const eqb_remap_desc* d) {
+  if (d->face_ptrs || d->src_stride_h < 6ll * d->w_face) return false;
+  for (int i = 0; i < 6; ++i)
+    if (d->cell_offset[i] != (long long)i * d->w_face) return false;
+  return true;
+}
+
 static bool can_stage(const eqb_remap_desc* d) {
   if (d->flags & EQB_FLAG_NO_STAGE) return false;
-  if (d->transform == EQB_CUBE2EQUI) {
-    // only a true horizon strip is one plain image the box loads can address; its
-    // cross-face tap bleed is then simply what the memory holds
-    if (d->face_ptrs || d->src_stride_h < 6ll * d->w_face) return false;
+  if (d->transform == EQB_CUBE2EQUI && !cube_is_horizon(d)) {
+    // a true horizon strip is one plain image (its cross-face tap bleed is simply what the
+    // memory holds); any other face canvas (dice, stacked faces) is staged face by face
+    // through per-face tensor maps; separate face tensors (face_ptrs) gather directly
+    const long long per16 = 16 / (long long)elt_size(d->dtype);
+    if (d->face_ptrs || (d->flags & EQB_FLAG_NO_TMA) || !tma_available()) return false;
+    if (d->w_face % per16 || d->w_face < 16) return false;
     for (int i = 0; i < 6; ++i)
-      if (d->cell_offset[i] != (long long)i * d->w_face) return false;
+      if (d->cell_offset[i] % per16) return false;
   }
   // pers2equi: most of the output lies outside the field of view and is a plain fill in
   // the direct kernel (no taps, no tile synchronisation): 1.7 ms vs 3.4 ms for 8 x 8K
@@ -215,6 +228,8 @@ static EncodeTiledFn encode_tiled() {
   }();
   return fn;
 }
+
+static bool tma_available() { return encode_tiled() != nullptr; }
 
 // ---- tensor-map cache ---------------------------------------------------------------------
 // Encoding a tensor map costs ~1 us and a staged launch needs up to 13 of them; repeated
@@ -312,6 +327,52 @@ static void setup_tma(const eqb_remap_desc* d, Params& p, bool lean) {
   for (int m = kTmaBoxes; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
   p.tma_batched = batched ? 1 : 0;
   p.use_tma = 1;
+}
+
+// cube2equi from a face canvas that is not a horizon strip: kFaceBoxes tensor maps per face
+// over the face viewed as (w, w, C, B) at src + cell_offset[f]; tmaps[f * kFaceBoxes + m].
+static void setup_tma_faces(const eqb_remap_desc* d, Params& p) {
+  p.use_tma = 0;
+  p.face_maps = 0;
+  if (!encode_tiled()) return;
+  const int elt = (int)elt_size(d->dtype);
+  const int per16 = 16 / elt;
+  CUtensorMapDataType dt = d->dtype == EQB_U8    ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                           : d->dtype == EQB_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                           : d->dtype == EQB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const bool batched = d->src_stride_b > 0 && d->batch > 1;
+  const cuuint64_t w = (cuuint64_t)d->w_face;
+  const cuuint64_t dims[4] = {w, w, (cuuint64_t)d->channels, (cuuint64_t)(batched ? d->batch : 1)};
+  const cuuint64_t row = (cuuint64_t)d->src_stride_h * elt;
+  const cuuint64_t cstride = d->channels > 1 ? (cuuint64_t)d->src_stride_c * elt : row * w;
+  const cuuint64_t strides[3] = {row, cstride,
+                                 batched ? (cuuint64_t)d->src_stride_b * elt
+                                         : cstride * d->channels};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0 || strides[i] % 16) return;
+  const int budget = staged_smem_bytes(elt) / elt / d->channels;
+  const int widths[kFaceBoxes] = {128, 96, 64};
+  for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
+  for (int m = 0; m < kFaceBoxes; ++m) {
+    const int bw = (widths[m] + per16 - 1) / per16 * per16;
+    const int bh = budget / bw < 128 ? budget / bw : 128;
+    if (bh < 8) return;
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)d->channels, 1};
+    for (int f = 0; f < 6; ++f) {
+      void* base = const_cast<char*>(static_cast<const char*>(d->src)) +
+                   (long long)d->cell_offset[f] * elt;
+      if (reinterpret_cast<uintptr_t>(base) % 16) return;
+      if (encode_cached(&p.tmaps[f * kFaceBoxes + m], dt, base, dims, strides, box) !=
+          CUDA_SUCCESS)
+        return;
+    }
+    p.tma_bw[m] = bw;
+    p.tma_bh[m] = bh;
+  }
+  p.tma_batched = batched ? 1 : 0;
+  p.use_tma = 1;
+  p.face_maps = 1;
 }
 
 // Fast coordinates (exact chain on every 4th pixel + cubic interpolation) are the
@@ -463,6 +524,11 @@ template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int 
     setup_tma_nhwc(d, p);
     if (!p.use_tma) return cudaErrorNotSupported;
     return launch_nhwc<XF>(p, s);
+  }
+  if (XF == EQB_CUBE2EQUI && can_stage(d) && !cube_is_horizon(d)) {
+    setup_tma_faces(d, p);
+    if (p.use_tma) return launch_staged<XF>(p, d->mode, d->dtype, false, false, s);
+    return launch_remap<XF>(p, d->mode, d->dtype, px, pick_ws(d), s);
   }
   if (can_stage(d)) {
     bool lean = can_lean(d);

@@ -122,6 +122,29 @@ def _minmax_views(views, device) -> torch.Tensor:
     return torch.stack([st[:, 0].min(), st[:, 1].max()])
 
 
+def _regular_faces(faces):
+    """If face f of item b lives at base + (b * SB + cell[f]) elements for every b, f:
+    (tensor at the lowest address, [cell offsets], SB); else None."""
+    esize = faces[0][0].element_size()
+    p0 = [f.data_ptr() for f in faces[0]]
+    base = min(p0)
+    cells = [(q - base) for q in p0]
+    if any(c % esize for c in cells):
+        return None
+    cells = [c // esize for c in cells]
+    sb = 0
+    if len(faces) > 1:
+        d = faces[1][0].data_ptr() - p0[0]
+        if d <= 0 or d % esize:
+            return None
+        sb = d // esize
+    for b, cube in enumerate(faces):
+        for f, t in enumerate(cube):
+            if t.data_ptr() != base + (b * sb + cells[f]) * esize:
+                return None
+    return faces[0][p0.index(base)], cells, sb
+
+
 def run(cubemap, cube_format, height, width, mode, clip_output=True,
         opt: K.Options = None) -> torch.Tensor:
     """Replaces convert2horizon + equilib/cube2equi/torch.py:248-357."""
@@ -167,7 +190,16 @@ def run(cubemap, cube_format, height, width, mode, clip_output=True,
         need_clip = (f0.dtype != torch.uint8 and clip_output
                      and (exact_clip or mode == "bicubic"))
         same_layout = all(f.stride() == f0.stride() for f in flat) and f0.stride(2) == 1
-        if same_layout and not need_clip:
+        regular = _regular_faces(faces) if (same_layout and not need_clip) else None
+        if regular is not None:
+            # zero-copy, and the faces sit at regular offsets in one allocation (e.g. the
+            # face-major buffer equi2cube returns its list / dict faces in): a canvas with six
+            # cell offsets, which the staged kernel reads through per-face TMA boxes
+            src, cells, batch_stride = regular
+            src_strides = (batch_stride, f0.stride(0), f0.stride(1))
+            clip_views = []
+            _keepalive = flat  # noqa: F841  (faces outlive the launch via the caller)
+        elif same_layout and not need_clip:
             # zero-copy: a device table of B x 6 face base pointers
             ptrs = torch.tensor([f.data_ptr() for f in flat], dtype=torch.int64)
             face_ptrs = ptrs.to(f0.device, non_blocking=True)
