@@ -1,0 +1,23 @@
+#!/bin/bash
+# One gpurun call: everything profiles/ needs, from the code as it is now.
+mkdir -p gpurun_out/ev
+O=gpurun_out/ev
+rm -f gpurun_out/parity_rates.jsonl
+python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+cp gpurun_out/parity_rates.jsonl $O/parity_rates.jsonl 2>/dev/null
+python bench.py > $O/bench_default.json 2> $O/bench_default.err
+python bench.py --impl reference --steps 10 --warmup 2 > $O/bench_reference.json 2>> $O/bench_default.err
+for w in e2e_4k_f32_b16 e2e_4k_u8_b32 e2p_8k_u8_bicubic_b8 p2e_8k_u8_bicubic_b8 e2p_multiview_f16_v256; do
+  python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline >> $O/bench_workloads.jsonl 2>> $O/bench_default.err
+done
+python bench.py --exact-coords --steps 20 --warmup 3 --no-cpu-baseline --no-e2e >> $O/bench_workloads.jsonl 2>> $O/bench_default.err
+python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
+python tools/rotation_sweep.py > $O/rotation_sweep.jsonl 2> $O/rotation_sweep.err
+python tools/validate_vs_reference_cuda.py --ref baseline/_ref > $O/validate.jsonl 2> $O/validate.err
+# launch list of the bench command (share of the step per kernel), then full captures
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launches.log 2>&1
+N=3 python tools/prof_one.py > $O/prof_plain.log 2>&1 && ncu --set full --import-source on --clock-control none -k regex:remap_lean2 -s 2 -c 1 -o $O/prof_bf16 -f python tools/prof_one.py > $O/ncu_bf16.log 2>&1
+DTYPE=f32 B=16 N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && DTYPE=f32 B=16 ncu --set full --import-source on --clock-control none -k regex:remap_lean2 -s 2 -c 1 -o $O/prof_f32 -f python tools/prof_one.py > $O/ncu_f32.log 2>&1
+DTYPE=u8 N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && DTYPE=u8 ncu --set full --import-source on --clock-control none -k regex:remap_lean -s 2 -c 1 -o $O/prof_u8 -f python tools/prof_one.py > $O/ncu_u8.log 2>&1
+MODE=bicubic N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && MODE=bicubic ncu --set full --import-source on --clock-control none -k regex:remap_staged -s 2 -c 1 -o $O/prof_bicubic -f python tools/prof_one.py > $O/ncu_bicubic.log 2>&1
+tail -3 $O/pytest_gpu.log

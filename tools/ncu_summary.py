@@ -30,6 +30,27 @@ KEYS = [
 ]
 
 
+def stamp():
+    """Identity of the code the capture was taken from: the library's source hash (what
+    bench.py prints as roofline.library_source_hash) and the git commit, when available."""
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    try:
+        from equilib_b200 import build
+
+        h = build.source_hash()
+    except Exception:
+        h = "?"
+    try:
+        g = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True,
+                           text=True).stdout.strip()
+    except Exception:
+        g = "?"
+    return f"library source hash {h} (tree at summary time), git {g or '?'}"
+
+
 def ncu(rep, page):
     out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True,
                          text=True).stdout
@@ -43,6 +64,7 @@ def main():
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     print("report:", rep)
     print("kernel:", d.get("Kernel Name", ("?",))[0])
+    print("stamp:", stamp())
     for k in KEYS:
         if k in d:
             print(f"{k:72s} {d[k][0]:>18s} {d[k][1]}")

@@ -58,7 +58,9 @@ def main():
         print(f"{c['total']:6d} " + " ".join(f"{c[op]:7d}" for op in OPS) + f"  {f} (max over {cnt} instantiations)")
     print("\nheadline instantiations:")
     for n, c in rows:
-        if re.search(r"remap_lean3_kernel<0, (__nv_bfloat16|float), 3|remap_lean_kernel<0, unsigned char, 0, 3>", n):
+        if re.search(r"remap_lean2_kernel<\(int\)0, (__nv_bfloat16, \(int\)3, \(bool\)0|float, \(int\)3, \(bool\)1)|"
+                     r"remap_lean_kernel<\(int\)0, unsigned char, \(int\)0, \(int\)3>|"
+                     r"remap_staged_kernel<\(int\)0, \(int\)2, __nv_bfloat16", n):
             print(f"{c['total']:6d} " + " ".join(f"{c[op]:7d}" for op in OPS) + f"  {n.replace('void ', '')[:90]}")
 
 
