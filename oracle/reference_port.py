@@ -4,9 +4,11 @@ TEST / BENCH INFRASTRUCTURE ONLY (see oracle/__init__.py): used by bench.py's
 ``cpu_baseline`` leg and ``--impl reference`` arm, and checked against
 oracle/remap_oracle.py in tests/test_reference_port.py.
 
-The reference itself (a Python package) cannot travel to the GPU box, so this file
-restates what its torch path *executes* on CPU tensors, op for op, so that its
-timing stands in for the reference's:
+bench.py times the UNMODIFIED reference package from baseline/_ref whenever that directory
+is present (it is git-ignored but travels with the repo snapshot; kind "reference").  This
+file is the fallback for a checkout without it (kind "port"): it restates what the
+reference's torch path *executes* on CPU tensors, op for op, so that its timing stands in
+for the reference's:
 
   equilib/equi2equi/torch.py:143-198   grid prep (cached, as the class API does)
                                         -> matmul -> convert_grid -> native() -> clip

@@ -15,9 +15,4 @@ python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
 python tools/rotation_sweep.py > $O/rotation_sweep.jsonl 2> $O/rotation_sweep.err
 python tools/validate_vs_reference_cuda.py --ref baseline/_ref > $O/validate.jsonl 2> $O/validate.err
 # launch list of the bench command (share of the step per kernel), then full captures
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launches.log 2>&1
-N=3 python tools/prof_one.py > $O/prof_plain.log 2>&1 && ncu --set full --import-source on --clock-control none -k regex:remap_lean2 -s 2 -c 1 -o $O/prof_bf16 -f python tools/prof_one.py > $O/ncu_bf16.log 2>&1
-DTYPE=f32 B=16 N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && DTYPE=f32 B=16 ncu --set full --import-source on --clock-control none -k regex:remap_lean2 -s 2 -c 1 -o $O/prof_f32 -f python tools/prof_one.py > $O/ncu_f32.log 2>&1
-DTYPE=u8 N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && DTYPE=u8 ncu --set full --import-source on --clock-control none -k regex:remap_lean -s 2 -c 1 -o $O/prof_u8 -f python tools/prof_one.py > $O/ncu_u8.log 2>&1
-MODE=bicubic N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && MODE=bicubic ncu --set full --import-source on --clock-control none -k regex:remap_staged -s 2 -c 1 -o $O/prof_bicubic -f python tools/prof_one.py > $O/ncu_bicubic.log 2>&1
 tail -3 $O/pytest_gpu.log
