@@ -1,0 +1,749 @@
+// STATUS: EXPERIMENT, NOT BUILT (round 2): remap_lean2.cuh with the 32 lanes of a warp on 32
+// ADJACENT pixels of ONE row (a lane owns one column in four rows) instead of 16 x 2 lanes.
+// The idea: a tap instruction then reads one run of source words instead of two runs from two
+// source rows.  Measured (profiles/r02_experiments/ncu_lean2_lanes32.txt): the tap loads still
+// take 1.63 wavefronts each -- the runs break wherever the sampling line crosses a source row,
+// and each break shifts the bank index by the row pitch -- while four row pointers per lane cost
+// instructions (1228 M vs 1097 M warp-instructions): 1.64 vs 1.37 ms on the headline workload.
+//
+// remap_lean2_kernel: the round-2 headline kernel -- bilinear, TMA-staged, planar 1 / 3 / 4
+// channels, equi2equi / equi2pers / equi2cube.  Designed from ncu captures of its predecessors
+// (profiles/r01_ncu_remap_bf16_v6_lean_final.txt: 147 instructions per pixel, L1 data pipe
+// 82 %, 2.3 wavefronts per 2-byte tap; profiles/r02_ncu_lean2_v1.txt: 5.3x the source bytes
+// fetched as TMA boxes, a fifth of all issued instructions spinning on the box barrier):
+//
+//  1. COORDINATES FROM A STRIP-WIDE NODE GRID.  A CTA walks a strip of up to 8 tiles
+//     (32 x 16 pixels each) along x.  Before the first tile all 128 threads evaluate the
+//     exact coordinate chain at the strip's NODES -- every 8th column of every row, plus one
+//     column on either side -- into shared memory (fully occupied warps: 1/8 node per pixel
+//     instead of the 1/4 of round 1, where every lane computed its own).  A pixel then gets
+//     (ui, uj) from the four nodes around it on its own row by cubic Lagrange interpolation
+//     with weights that are LANE CONSTANTS (a lane's pixels all sit at the same offset inside
+//     their 8-pixel interval), as differences from the nearest node: 4 LDS.64 + 3 packed
+//     subtractions + 3 FFMA2 per pixel, no shuffles, no weight loads.
+//  2. PER-TILE HEADERS.  The same prologue reduces each tile's node hull to its TMA box
+//     (origin, shape) and to flags -- smooth (4th and 2nd differences of the nodes small: the
+//     interpolation error is below 1e-3 px and no pixel leaves the node hull by more than
+//     1/4 px, so no per-pixel "inside the box" test is needed), border (a clamp, the wrap or
+//     the footprint shift at the last column could trigger), seam.  Smooth interior tiles
+//     with a box take a straight-line fast path: no reductions, votes, clamps or wraps.
+//  3. SQUARER TILES, TWO BOX BUFFERS.  A 32 x 16 tile of a view rolled by 0.3 rad needs a
+//     48 x 30 box where the 64 x 8 tile of round 1 needed 96 x 40: less than half the L2 ->
+//     shared traffic per pixel.  The box of the NEXT tile is requested while the current one
+//     is blended (two buffers, full / empty mbarriers per buffer, no __syncthreads in the tile
+//     loop, waits back off with nanosleep instead of spinning on the issue slots).
+//  4. ALIGNED-WORD TAPS.  The 16 lanes of a row read 16 ADJACENT source pixels per tap
+//     instruction.  A 1- or 2-byte tap is fetched as the aligned 32-bit word that holds it
+//     (lanes sharing a word read the same address: a broadcast, one wavefront) and moved
+//     into place by one PRMT with a per-pixel selector -- the same two instructions as
+//     LDS.U16 + shift, without the extra wavefronts of sub-word accesses (measured: 1.7 per
+//     LDS.U16 when neighbouring lanes read the two halves of one word).
+//
+// Tiles that are not smooth (source poles), border / seam / ragged tiles and the EXACT variant
+// evaluate the exact chain on every pixel; tiles whose footprint fits no box (poles, seam)
+// gather from global memory -- same values on every path
+// (tests: test_staged_and_direct_kernels_agree).
+#pragma once
+
+#include "remap_kernels.cuh"
+
+namespace eqb {
+
+#ifndef EQB_L2_BUF_KB
+#define EQB_L2_BUF_KB 12
+#endif
+constexpr int kL2Warps = 4;
+constexpr int kL2TileW = 32, kL2TileH = 16;
+constexpr int kL2Step = 8;                          // node spacing along x
+constexpr int kL2MaxIters = 8;                      // tiles per strip
+constexpr int kL2Cols = kL2MaxIters * 4 + 3;        // node columns -1 .. 4 * iters + 1
+constexpr int kL2Boxes = 11;
+constexpr int kL2MinBoxH = kL2TileH + 5;            // an upright tile: 16 rows + 1 + margins
+static_assert(kL2Boxes <= kTmaSlots, "tensor-map slots");
+
+// One box buffer (a CTA holds two).
+#ifndef EQB_L2_LANES32
+#define EQB_L2_LANES32 1  // experiments: 0 = the 16 x 2 lane shape
+#endif
+#ifndef EQB_L2_BUF_KB_F32
+#define EQB_L2_BUF_KB_F32 18  // (measured 16 / 18 / 20 KB: 1.17 / 1.10 / 1.13 ms on 16 x 4K fp32, bench rotations)
+#endif
+EQB_HD constexpr int l2_buf_bytes(int elt) { return elt == 4 ? EQB_L2_BUF_KB_F32 * 1024 : 12 * 1024; }
+// CTAs per SM the shared memory allows (two buffers + ~6 KB of nodes, headers, reserve)
+EQB_HD constexpr int l2_ctas(int elt) { return 227 * 1024 / (2 * l2_buf_bytes(elt) + 6 * 1024); }
+
+// Box m: l2_box_w x l2_box_h source pixels x channels.  Boxes 0-1 are small (upright and
+// mildly rolled views); the others spend the whole buffer in different aspect ratios: 48
+// wide for rolls, 64-96 for the longitude stretch 1 / cos(lat) at high source latitudes,
+// 40 / 32 for rolls beyond 45 degrees.  pick = the first that fits.
+EQB_HD constexpr int l2_box_w(int elt, int m) {
+  const int w = m <= 2 ? 48 : m == 3 ? 64 : m == 4 ? 56 : m == 5 ? 80 : m == 6 ? 72 :
+                m == 7 ? 88 : m == 8 ? 96 : m == 9 ? 40 : 32;
+  const int per16 = 16 / elt;
+  return (w + per16 - 1) / per16 * per16;
+}
+EQB_HD constexpr int l2_box_h(int elt, int nc, int m) {
+  const int budget = l2_buf_bytes(elt) / elt / nc;
+  const int full = budget / l2_box_w(elt, m) < 128 ? budget / l2_box_w(elt, m) : 128;
+  const int small = m == 0 ? 24 : 32;
+  return m < 2 && small < full ? small : full;
+}
+
+// Cubic Lagrange weights of the nodes at -8, 0, +8, +16 for the pixel at offset t (0..7)
+// from the second one; the weight of that node is not stored (the weights sum to 1:
+// u = n1 + sum w_j (n_j - n1)).
+struct L2Weights { float w[8][3]; };
+constexpr L2Weights make_l2_weights() {
+  L2Weights r{};
+  for (int t = 0; t < 8; ++t) {
+    const double s = t / 8.0;
+    r.w[t][0] = (float)(-s * (s - 1.0) * (s - 2.0) / 6.0);
+    r.w[t][1] = (float)(-(s + 1.0) * s * (s - 2.0) / 2.0);
+    r.w[t][2] = (float)((s + 1.0) * s * (s - 1.0) / 6.0);
+  }
+  return r;
+}
+static __device__ const L2Weights g_l2_weights = make_l2_weights();
+
+enum : int { L2_SMOOTH = 1, L2_BORDER = 2, L2_STRADDLE = 4, L2_RAGGED = 8, L2_BACKGROUND = 16 };
+
+// (barriers are addressed by their 32-bit shared-memory address, computed once per kernel:
+// re-deriving it from a generic pointer at every use was 3 % of the issued instructions)
+__device__ __forceinline__ void mbar_arrive(unsigned bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+// Wait on a phase: try_wait suspends the warp in hardware up to the time hint, so the loop
+// around it rarely iterates (the earlier probe + nanosleep(32) loop spent 8 % of the issued
+// instructions spinning).
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar_addr, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar_addr), "r"(parity) : "memory");
+}
+
+// Rays of the cube faces as coded in torch_utils/grid.py:137-171 (F R B L U D).
+__device__ __forceinline__ void cube_ray(int face, float rc, float rr, float& mx, float& my,
+                                         float& mz) {
+  switch (face) {
+    case 0: mx = 0.5f; my = rc; mz = -rr; break;
+    case 1: mx = -rc; my = 0.5f; mz = -rr; break;
+    case 2: mx = -0.5f; my = -rc; mz = -rr; break;
+    case 3: mx = rc; my = -0.5f; mz = -rr; break;
+    case 4: mx = rr; my = rc; mz = 0.5f; break;
+    default: mx = -rr; my = rc; mz = -0.5f; break;
+  }
+}
+
+// Coordinates of a NODE: column x may lie up to 8 pixels outside the image (the map is
+// continued smoothly: longitude is periodic, the pinhole grid and the cube-face ramp are
+// linear).  Nodes only feed the interpolation and the boxes, never a pixel directly -- except
+// where x is a pixel column, and there this is the exact chain.
+template <int XF>
+__device__ __forceinline__ void node_coords(const Params& p, const RowCtx<XF>& c, int x, int y,
+                                            int cell, float& uj, float& ui) {
+  if (XF == EQB_EQUI2EQUI) {
+    const int xw = x < 0 ? x + p.dw : (x >= p.dw ? x - p.dw : x);
+    coords<XF, false>(p, c, 0, xw, y, 0, 0, uj, ui);
+  } else if (XF == EQB_EQUI2PERS) {
+    coords<XF, false>(p, c, 0, x, y, 0, 0, uj, ui);
+  } else {  // EQB_EQUI2CUBE
+    const int w = p.w_face, lx = x - cell * w;
+    float rcol;
+    if (lx >= 0 && lx < w) {
+      rcol = __ldg(p.tx + lx);
+    } else {
+      const float step = __ldg(p.tx + 1) - __ldg(p.tx);
+      rcol = lx < 0 ? fmaf((float)lx, step, __ldg(p.tx))
+                    : fmaf((float)(lx - (w - 1)), step, __ldg(p.tx + w - 1));
+    }
+    float mx, my, mz, X, Y, Z, phi, theta;
+    cube_ray(cell, rcol, c.r0, mx, my, mz);
+    rotate(c.A, mx, my, mz, X, Y, Z);
+    spherical<false>(X, Y, Z, phi, theta);
+    tail_minus_half<false>(phi, theta, p.shf, p.swf, uj, ui);
+  }
+}
+
+// Two nodes of one row at once (the packed chain, coords2).
+template <int XF>
+__device__ __forceinline__ void node_coords2(const Params& p, const RowCtx<XF>& c, int x0, int x1,
+                                             int cell, float (&ui)[2], float (&uj)[2]) {
+  if (XF == EQB_EQUI2EQUI) {
+    const int xa = x0 < 0 ? x0 + p.dw : (x0 >= p.dw ? x0 - p.dw : x0);
+    const int xb = x1 < 0 ? x1 + p.dw : (x1 >= p.dw ? x1 - p.dw : x1);
+    coords2<XF, false>(p, c, xa, xb, 0, 0.f, 0.f, ui, uj);
+  } else if (XF == EQB_EQUI2PERS) {
+    coords2<XF, false>(p, c, x0, x1, 0, 0.f, 0.f, ui, uj);
+  } else {  // EQB_EQUI2CUBE: the ramp continued linearly outside the face
+    const int w = p.w_face;
+    float rc[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int lx = (i ? x1 : x0) - cell * w;
+      if (lx >= 0 && lx < w) {
+        rc[i] = __ldg(p.tx + lx);
+      } else {
+        const float step = __ldg(p.tx + 1) - __ldg(p.tx);
+        rc[i] = lx < 0 ? fmaf((float)lx, step, __ldg(p.tx))
+                       : fmaf((float)(lx - (w - 1)), step, __ldg(p.tx + w - 1));
+      }
+    }
+    coords2<XF, false>(p, c, x0, x1, cell, rc[0], rc[1], ui, uj);
+  }
+}
+
+// ---- taps --------------------------------------------------------------------------------
+// Sampling state of one pixel on the fast path: the word addresses of its left and right taps
+// (row y0, channel 0) and the PRMT selectors that move the tap out of its word.
+struct L2Px {
+  unsigned a0, a1;  // shared-memory byte addresses
+  unsigned s0, s1;  // PRMT selectors (fp16 / fp32: unused)
+};
+
+template <typename T>
+__device__ __forceinline__ void l2_px_setup(unsigned a, L2Px& q) {
+  if (sizeof(T) == 2 && !cuda::std::is_same<T, __half>::value) {
+    // bf16 -> fp32 is "the 16 bits in the upper half": selector 0x1044 lifts the low half of
+    // the word ([0, 0, b0, b1]), 0x3244 keeps the high half ([0, 0, b2, b3])
+    q.a0 = a & ~3u;
+    q.a1 = (a + 2u) & ~3u;
+    q.s0 = (a & 2u) ? 0x3244u : 0x1044u;
+    q.s1 = q.s0 ^ 0x2200u;
+  } else if (sizeof(T) == 1) {
+    // byte k of the word into byte 0 of 0x4B0000kk = 2^23 + k
+    q.a0 = a & ~3u;
+    q.a1 = (a + 1u) & ~3u;
+    q.s0 = 0x7540u | (a & 3u);
+    q.s1 = 0x7540u | ((a + 1u) & 3u);
+  } else {
+    q.a0 = a;
+    q.a1 = a + (unsigned)sizeof(T);
+    q.s0 = q.s1 = 0u;
+  }
+}
+
+// The tap at compile-time byte offset OFF (row / channel) from word address `addr`.
+template <typename T, int OFF>
+__device__ __forceinline__ float l2_tap(unsigned addr, unsigned sel) {
+  if (sizeof(T) == 4) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+  }
+  if (cuda::std::is_same<T, __half>::value) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(addr), "n"(OFF));
+    return __half2float(__ushort_as_half(v));
+  }
+  unsigned w;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w) : "r"(addr), "n"(OFF));
+  if (sizeof(T) == 1)
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, sel)), 8388608.0f);
+  return __uint_as_float(__byte_perm(w, 0u, sel));
+}
+
+// Store of a lane's four results of one channel: pixel j at d + off[j], where bit j of `ok`
+// is set (2- and 4-byte types).
+template <typename T>
+__device__ __forceinline__ void l2_store(T* d, const long long (&off)[4], unsigned ok,
+                                         const float (&o)[4]) {
+  static_assert(sizeof(T) >= 2, "uint8 runs the round-1 lean kernel");
+  if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (ok & (1u << j)) __stcs(reinterpret_cast<float*>(d + off[j]), o[j]);
+  } else {
+    unsigned lo, hi;
+    if constexpr (cuda::std::is_same<T, __half>::value) {
+      const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+      lo = *reinterpret_cast<const unsigned*>(&a);
+      hi = *reinterpret_cast<const unsigned*>(&b);
+    } else {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(o[2], o[3]);
+      lo = *reinterpret_cast<const unsigned*>(&a);
+      hi = *reinterpret_cast<const unsigned*>(&b);
+    }
+    if (ok & 1u) __stcs(reinterpret_cast<unsigned short*>(d + off[0]), (unsigned short)lo);
+    if (ok & 2u) __stcs(reinterpret_cast<unsigned short*>(d + off[1]), (unsigned short)(lo >> 16));
+    if (ok & 4u) __stcs(reinterpret_cast<unsigned short*>(d + off[2]), (unsigned short)hi);
+    if (ok & 8u) __stcs(reinterpret_cast<unsigned short*>(d + off[3]), (unsigned short)(hi >> 16));
+  }
+}
+
+// Blend + store of one channel from box M: pixel pairs (0, 1) and (2, 3) share FFMA2s.
+template <typename T, int M, int NC, int CI>
+__device__ __forceinline__ void l2_blend_channel(const L2Px (&q)[4],
+                                                 const unsigned long long (&w_nw)[2],
+                                                 const unsigned long long (&w_ne)[2],
+                                                 const unsigned long long (&w_sw)[2],
+                                                 const unsigned long long (&w_se)[2], T* d,
+                                                 const long long (&off)[4], unsigned ok,
+                                                 long long dsc) {
+  constexpr int ELT = (int)sizeof(T);
+  constexpr int ROW = l2_box_w(ELT, M) * ELT;
+  constexpr int CH = CI * ROW * l2_box_h(ELT, NC, M);
+  float o[4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const L2Px &x = q[2 * k], &y = q[2 * k + 1];
+    unsigned long long acc =
+        mul2(pk2(l2_tap<T, CH>(x.a0, x.s0), l2_tap<T, CH>(y.a0, y.s0)), w_nw[k]);
+    acc = fma2(pk2(l2_tap<T, CH>(x.a1, x.s1), l2_tap<T, CH>(y.a1, y.s1)), w_ne[k], acc);
+    acc = fma2(pk2(l2_tap<T, CH + ROW>(x.a0, x.s0), l2_tap<T, CH + ROW>(y.a0, y.s0)), w_sw[k], acc);
+    acc = fma2(pk2(l2_tap<T, CH + ROW>(x.a1, x.s1), l2_tap<T, CH + ROW>(y.a1, y.s1)), w_se[k], acc);
+    unpk2(acc, o[2 * k], o[2 * k + 1]);
+  }
+  l2_store<T>(d + CI * dsc, off, ok, o);
+}
+
+template <typename T, int M, int NC>
+__device__ __forceinline__ void l2_blend(const L2Px (&q)[4], const float (&fx)[4],
+                                         const float (&fy)[4], T* d, const long long (&off)[4],
+                                         unsigned ok, long long dsc) {
+  const unsigned long long one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
+  unsigned long long w_nw[2], w_ne[2], w_sw[2], w_se[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const unsigned long long bx = pk2(fx[2 * k], fx[2 * k + 1]), by = pk2(fy[2 * k], fy[2 * k + 1]);
+    const unsigned long long ax = fma2(bx, mone, one), ay = fma2(by, mone, one);  // 1 - b, exact
+    w_nw[k] = mul2(ax, ay);
+    w_ne[k] = mul2(bx, ay);
+    w_sw[k] = mul2(ax, by);
+    w_se[k] = mul2(bx, by);
+  }
+  l2_blend_channel<T, M, NC, 0>(q, w_nw, w_ne, w_sw, w_se, d, off, ok, dsc);
+  if constexpr (NC > 1) l2_blend_channel<T, M, NC, 1>(q, w_nw, w_ne, w_sw, w_se, d, off, ok, dsc);
+  if constexpr (NC > 2) l2_blend_channel<T, M, NC, 2>(q, w_nw, w_ne, w_sw, w_se, d, off, ok, dsc);
+  if constexpr (NC > 3) l2_blend_channel<T, M, NC, 3>(q, w_nw, w_ne, w_sw, w_se, d, off, ok, dsc);
+}
+
+template <int XF, typename T, int NC, bool EXACT>
+__global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 5 ? l2_ctas(4) : 5) : (EXACT ? 5 : 7))
+    remap_lean2_kernel(const __grid_constant__ Params p) {
+  constexpr int ELT = (int)sizeof(T);
+  constexpr int PER16 = 16 / ELT;
+  constexpr int P = 1;  // (pixels per lane and row; uint8 runs the round-1 lean kernel)
+  constexpr int BUF = l2_buf_bytes(ELT);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];  // two box buffers
+  __shared__ __align__(16) float2 nodes[kL2TileH][kL2Cols + 1];  // (ui, uj)
+  __shared__ __align__(16) int4 headers[kL2MaxIters];
+  __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int tile_y0 = blockIdx.y * kL2TileH;
+  const int strip_x0 = blockIdx.x * p.iters * kL2TileW;
+  const int ntiles = min(p.iters, (p.dw - strip_x0 + kL2TileW - 1) / kL2TileW);
+  int cell = 0;
+  if (XF == EQB_EQUI2CUBE) cell = strip_x0 / p.w_face;  // (a strip never straddles two cells)
+  const bool background = XF == EQB_EQUI2CUBE && cell >= 6;
+
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], kL2Warps);
+    mbar_init(&empty_bar[1], kL2Warps);
+  }
+
+  // ---- prologue 1: the exact chain at the strip's nodes -------------------------------
+  if (!background) {
+    const int row = tid & (kL2TileH - 1);
+    const int y = min(tile_y0 + row, p.dh - 1);
+    RowCtx<XF> rc;
+    row_setup<XF>(p, b, y, rc);
+    const int ncols = ntiles * 4 + 3;
+    constexpr int STEP = kL2Warps * 32 / kL2TileH;  // columns a thread advances by
+    if constexpr (EXACT) {
+      // two nodes per packed chain (coords2)
+      for (int col = tid >> 4; col < ncols; col += 2 * STEP) {
+        const int col2 = col + STEP < ncols ? col + STEP : col;
+        float ui[2], uj[2];
+        node_coords2<XF>(p, rc, strip_x0 + kL2Step * (col - 1), strip_x0 + kL2Step * (col2 - 1),
+                         cell, ui, uj);
+        nodes[row][col] = make_float2(ui[0], uj[0]);
+        nodes[row][col2] = make_float2(ui[1], uj[1]);
+      }
+    } else {
+      // (the packed chain is slower here: 1.41 vs 1.37 ms on the headline workload -- this
+      // variant runs at 72 registers for 7 CTAs per SM)
+      for (int col = tid >> 4; col < ncols; col += STEP) {
+        float uj, ui;
+        node_coords<XF>(p, rc, strip_x0 + kL2Step * (col - 1), y, cell, uj, ui);
+        nodes[row][col] = make_float2(ui, uj);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- prologue 2: one header per tile (warp w: tiles w, w + 4) -------------------------
+  {
+    // lane m holds the shape of box m
+    const int my_box = lane < kL2Boxes ? (p.tma_bw[lane & 15] | (p.tma_bh[lane & 15] << 16)) : 0;
+    for (int k = warp; k < ntiles; k += kL2Warps) {
+      int flags = 0;
+      if (strip_x0 + (k + 1) * kL2TileW > p.dw || tile_y0 + kL2TileH > p.dh) flags |= L2_RAGGED;
+      if (background) {
+        if (lane == 0) headers[k] = make_int4(0, 0, -1, flags | L2_BACKGROUND);
+        continue;
+      }
+      // window of five nodes centred on tile-local node column c = 1 or 3 of row r: the
+      // tile's own columns are 0..4, the windows also see -1 and 5 (interpolation stencils)
+      const int r = lane & 15, c = 1 + 2 * (lane >> 4);
+      const float2* np = &nodes[r][k * 4 + c - 1];  // (array index = node column + 1)
+      float2 n[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) n[i] = np[i];
+      float ulo = fminf(fminf(n[1].x, n[2].x), n[3].x), uhi = fmaxf(fmaxf(n[1].x, n[2].x), n[3].x);
+      float vlo = fminf(fminf(n[1].y, n[2].y), n[3].y), vhi = fmaxf(fmaxf(n[1].y, n[2].y), n[3].y);
+      const float2 e = c == 1 ? n[4] : n[0];  // the end node that is a column of the tile
+      ulo = fminf(ulo, e.x); uhi = fmaxf(uhi, e.x);
+      vlo = fminf(vlo, e.y); vhi = fmaxf(vhi, e.y);
+      const float2 f = c == 1 ? n[0] : n[4];  // the one outside
+      const float alo = fminf(ulo, f.x), ahi = fmaxf(uhi, f.x);
+      // (coordinates are >= 0: their bit patterns order like integers)
+      const float umin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(ulo)));
+      const float umax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(uhi)));
+      const float vmin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(vlo)));
+      const float vmax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(vhi)));
+      const float amin = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(alo)));
+      const float amax = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(ahi)));
+      // the tile's own footprint wraps around the seam (no single box holds it) / some node of
+      // its interpolation stencils lies across the seam (such tiles take the exact chain)
+      const bool box_straddle = umax - umin >= 0.5f * p.swf;
+      const bool straddle = amax - amin >= 0.5f * p.swf;
+      // smoothness: 4th difference (the cubic's error is ~0.023 of it) and 2nd difference (a
+      // pixel leaves the hull of its neighbouring nodes by at most 1/8 of it), from differences
+      // against the centre node (no cancellation at coordinates of order 4096)
+      bool ok = !straddle;
+      {
+        const float ax = n[0].x - n[2].x, bx = n[1].x - n[2].x, cx = n[3].x - n[2].x,
+                    dx = n[4].x - n[2].x;
+        const float ay = n[0].y - n[2].y, by = n[1].y - n[2].y, cy = n[3].y - n[2].y,
+                    dy = n[4].y - n[2].y;
+        const float d4x = (ax + dx) - 4.0f * (bx + cx), d4y = (ay + dy) - 4.0f * (by + cy);
+        const float d2x = bx + cx, d2y = by + cy;
+        ok = ok && fmaxf(fabsf(d4x), fabsf(d4y)) < 0.03f && fmaxf(fabsf(d2x), fabsf(d2y)) < 1.5f;
+      }
+      if (__all_sync(0xffffffffu, ok)) flags |= L2_SMOOTH;
+      if (straddle) flags |= L2_STRADDLE;
+      if (umin < 1.0f || umax > p.swm1f - 2.0f || vmin < 1.0f || vmax > p.shm1f - 2.0f)
+        flags |= L2_BORDER;
+      // box: top-left taps of the hull (with the footprint shift at the last column / row),
+      // one more pixel right and down, margin 2
+      const int bx0 = (int)fminf(floorf(fminf(umin, p.swm1f)), p.swm1f - 1.0f);
+      const int bx1 = (int)fminf(floorf(fminf(umax, p.swm1f)), p.swm1f - 1.0f);
+      const int by0 = (int)fminf(floorf(fminf(vmin, p.shm1f)), p.shm1f - 1.0f);
+      const int by1 = (int)fminf(floorf(fminf(vmax, p.shm1f)), p.shm1f - 1.0f);
+      const int gx0 = (bx0 - 2) & ~(PER16 - 1);  // 16-byte aligned (TMA requirement)
+      const int gy0 = by0 - 2;
+      const int need_w = bx1 + 4 - gx0, need_h = by1 + 4 - gy0;
+      const unsigned fit = __ballot_sync(
+          0xffffffffu, need_w <= (my_box & 0xffff) && need_h <= (my_box >> 16));
+      const int m = (box_straddle || !p.use_tma) ? -1 : __ffs(fit) - 1;
+      if (lane == 0) headers[k] = make_int4(gx0, gy0, m, flags);
+    }
+  }
+  __syncthreads();
+
+  // ---- tile loop ---------------------------------------------------------------------------
+  // Lane mapping.  EQB_L2_LANES32 (default): the 32 lanes of a warp are 32 ADJACENT pixels of
+  // one row and a lane owns column `lane` in the four rows 4w .. 4w + 3 -- a tap instruction
+  // then reads ONE run of 16 s + 1 words (s = local stretch), conflict-free up to s = 2.  The
+  // earlier 16 x 2 shape (rows 4w + ly, 4w + ly + 2; columns lx, lx + 16) put two runs from
+  // two source rows into every tap instruction: 1.6 wavefronts per LDS on the headline
+  // workload (profiles/r02_ncu_lean2_bf16_headline.txt, L1 data pipe 80 %).
+  constexpr bool RM = EQB_L2_LANES32 != 0;
+  const int lx = RM ? lane : (lane & 15), ly = RM ? 0 : (lane >> 4);
+  auto prow = [&](int j) { return RM ? warp * 4 + j : warp * 4 + ly + 2 * (j >> 1); };
+  auto xloc = [&](int j) { return RM ? lx : lx + 16 * (j & 1); };
+  auto piv = [&](int j) { return RM ? (lx >> 3) : (lx >> 3) + 2 * (j & 1); };
+  const int y0q = tile_y0 + prow(0);
+  const unsigned tile_s = smem_u32(smem_raw);
+  const unsigned full_s = smem_u32(&full_bar[0]), empty_s = smem_u32(&empty_bar[0]);
+  const T* const src_b = static_cast<const T*>(p.src) + (long long)b * p.ssb;
+  T* const dst_b = static_cast<T*>(p.dst) + (long long)b * p.dsb;
+  const int ssh = (int)p.ssh;
+  // element offsets of this lane's four pixels from its pixel 0, rows that exist
+  long long poff[4];
+  unsigned rows_ok = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    poff[j] = (long long)(prow(j) - prow(0)) * p.dsh + (xloc(j) - xloc(0));
+    if (tile_y0 + prow(j) < p.dh) rows_ok |= 1u << j;
+  }
+  // interpolation weights of this lane's pixels (offset t inside their 8-pixel interval)
+  unsigned long long wt[P][3];
+#pragma unroll
+  for (int q = 0; q < P; ++q) {
+    const int t = (lx * P + q) & 7;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) wt[q][j] = pk2(g_l2_weights.w[t][j], g_l2_weights.w[t][j]);
+  }
+
+  // The box of boxed tile n lives in buffer n & 1; phase parity of its barriers (n >> 1) & 1.
+  // Thread 0 requests the box of the NEXT boxed tile while the current one is blended.
+  auto issue = [&](int k, unsigned n) {  // thread 0 only
+    const int4 h = headers[k];
+    const unsigned buf = n & 1u;
+    if (n >= 2) mbar_wait_backoff(empty_s + buf * 8u, ((n >> 1) - 1u) & 1u);
+    mbar_expect_tx(&full_bar[buf], (unsigned)(p.tma_bw[h.z] * p.tma_bh[h.z] * NC * ELT));
+    tma_load_box(smem_raw + buf * BUF, &p.tmaps[h.z], &full_bar[buf], h.x, h.y, 0,
+                 p.tma_batched ? b : 0);
+  };
+  auto next_boxed = [&](int k) {
+    for (++k; k < ntiles; ++k)
+      if (headers[k].z >= 0) return k;
+    return -1;
+  };
+  unsigned nbox = 0;
+  if (tid == 0) {
+    const int k0 = next_boxed(-1);
+    if (k0 >= 0) issue(k0, 0);
+  }
+
+  for (int k = 0; k < ntiles; ++k) {
+    const int4 hdr = headers[k];
+    const int gx0 = hdr.x, gy0 = hdr.y, m = hdr.z, flags = hdr.w;
+    const int tile_x0 = strip_x0 + k * kL2TileW;
+    const bool boxed = m >= 0;
+    T* d0 = dst_b + (long long)min(y0q, p.dh - 1) * p.dsh + tile_x0 + xloc(0);
+    if (XF == EQB_EQUI2CUBE)
+      d0 = dst_b + (long long)min(y0q, p.dh - 1) * p.dsh + p.cell_off[cell] +
+           (tile_x0 - cell * p.w_face) + xloc(0);
+    // pixels of this lane that exist (ragged tiles: rows and columns beyond the image)
+    unsigned ok = rows_ok;
+    if (flags & L2_RAGGED) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (tile_x0 + xloc(j) >= p.dw) ok &= ~(1u << j);
+    }
+
+    if (flags & L2_BACKGROUND) {  // dice background cell
+      const float z[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < NC; ++c) l2_store<T>(d0 + c * p.dsc, poff, ok, z);
+      continue;
+    }
+
+    const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED)) == L2_SMOOTH
+                                      : (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE |
+                                                  L2_RAGGED)) == L2_SMOOTH);
+    if (fast) {
+      // ======== fast path: smooth tile with a box ==========================================
+      float ixa[4], iya[4];
+      if constexpr (!EXACT) {
+        const unsigned long long mone = pk2(-1.0f, -1.0f);
+#pragma unroll
+        for (int g = 0; g < 4 / P; ++g) {
+          const int r = prow(g);
+          const int iv = piv(g);
+          const unsigned long long* np =
+              reinterpret_cast<const unsigned long long*>(&nodes[r][k * 4 + iv]);
+          const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+          const unsigned long long d0n = fma2(n1, mone, n0), d2n = fma2(n1, mone, n2),
+                                   d3n = fma2(n1, mone, n3);
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const unsigned long long u =
+                fma2(wt[q][2], d3n, fma2(wt[q][1], d2n, fma2(wt[q][0], d0n, n1)));
+            unpk2(u, ixa[g * P + q], iya[g * P + q]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {  // pixel pairs (2g, 2g + 1): one packed chain each
+          float i2[2], j2[2];
+          if constexpr (RM) {  // one column, two rows
+            RowCtx<XF> ra, rb;
+            row_setup<XF>(p, b, min(tile_y0 + prow(2 * g), p.dh - 1), ra);
+            row_setup<XF>(p, b, min(tile_y0 + prow(2 * g + 1), p.dh - 1), rb);
+            const int xa = tile_x0 + xloc(0);
+            const float rca = XF == EQB_EQUI2CUBE ? __ldg(p.tx + (xa - cell * p.w_face)) : 0.f;
+            coords2r<XF, true>(p, ra, rb, xa, cell, rca, i2, j2);
+          } else {  // one row, two columns
+            RowCtx<XF> rc;
+            row_setup<XF>(p, b, min(tile_y0 + prow(2 * g), p.dh - 1), rc);
+            const int xa = tile_x0 + xloc(2 * g), xb = tile_x0 + xloc(2 * g + 1);
+            float rca = 0.f, rcb = 0.f;
+            if (XF == EQB_EQUI2CUBE) {
+              rca = __ldg(p.tx + (xa - cell * p.w_face));
+              rcb = __ldg(p.tx + (xb - cell * p.w_face));
+            }
+            coords2<XF, true>(p, rc, xa, xb, cell, rca, rcb, i2, j2);
+          }
+          ixa[2 * g] = i2[0]; ixa[2 * g + 1] = i2[1];
+          iya[2 * g] = j2[0]; iya[2 * g + 1] = j2[1];
+        }
+      }
+      L2Px px[4];
+      float fx[4], fy[4];
+      {
+        const int pitch = p.tma_bw[m];
+        const float pitchf = (float)pitch;
+        // byte address = ((yf - gy0) * pitch + (xf - gx0)) * ELT + buffer; yf * pitch + xf is
+        // an exact integer below 2^24
+        const int base = (int)(tile_s + (nbox & 1u) * BUF) - (gy0 * pitch + gx0) * ELT;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float xf = floorf(ixa[j]), yf = floorf(iya[j]);
+          if (EXACT) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
+            xf = fminf(xf, p.swm1f - 1.0f);
+            yf = fminf(yf, p.shm1f - 1.0f);
+          }
+          fx[j] = __fsub_rn(ixa[j], xf);
+          fy[j] = __fsub_rn(iya[j], yf);
+          l2_px_setup<T>((unsigned)((int)fmaf(yf, pitchf, xf) * ELT + base), px[j]);
+        }
+      }
+      // request the next box, then wait for this one
+      if (tid == 0) {
+        const int k2 = next_boxed(k);
+        if (k2 >= 0) issue(k2, nbox + 1);
+      }
+      __syncwarp();
+      mbar_wait_backoff(full_s + (nbox & 1u) * 8u, (nbox >> 1) & 1u);
+      {
+        auto blend_m = [&](auto mc) {
+          constexpr int M = decltype(mc)::value;
+          l2_blend<T, M, NC>(px, fx, fy, d0, poff, ok, p.dsc);
+        };
+        switch (m) {
+          case 0: blend_m(cuda::std::integral_constant<int, 0>{}); break;
+          case 1: blend_m(cuda::std::integral_constant<int, 1>{}); break;
+          case 2: blend_m(cuda::std::integral_constant<int, 2>{}); break;
+          case 3: blend_m(cuda::std::integral_constant<int, 3>{}); break;
+          case 4: blend_m(cuda::std::integral_constant<int, 4>{}); break;
+          case 5: blend_m(cuda::std::integral_constant<int, 5>{}); break;
+          case 6: blend_m(cuda::std::integral_constant<int, 6>{}); break;
+          case 7: blend_m(cuda::std::integral_constant<int, 7>{}); break;
+          case 8: blend_m(cuda::std::integral_constant<int, 8>{}); break;
+          case 9: blend_m(cuda::std::integral_constant<int, 9>{}); break;
+          default: blend_m(cuda::std::integral_constant<int, 10>{}); break;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + (nbox & 1u) * 8u);
+      ++nbox;
+      continue;
+    }
+
+    // ======== general path: taps from the box where they lie inside it, else from global
+    // memory.  Coordinates: interpolated like on the fast path where the tile is smooth and
+    // interior (a footprint too wide for any box -- high source latitudes -- is usually still
+    // smooth), the exact chain elsewhere (source poles, source border, seam, EXACT).
+    if (boxed) {
+      if (tid == 0) {
+        const int k2 = next_boxed(k);
+        if (k2 >= 0) issue(k2, nbox + 1);
+      }
+      __syncwarp();
+      mbar_wait_backoff(full_s + (nbox & 1u) * 8u, (nbox >> 1) & 1u);
+    }
+    {
+      const int pitch = boxed ? p.tma_bw[m] : 0;
+      const int bh = boxed ? p.tma_bh[m] : 0;
+      const T* const box = reinterpret_cast<const T*>(smem_raw + (nbox & 1u) * BUF);
+      const bool interp = !EXACT && (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE)) == L2_SMOOTH;
+      float ixa[4], iya[4];
+      if (interp) {
+        const unsigned long long mone = pk2(-1.0f, -1.0f);
+#pragma unroll
+        for (int g = 0; g < 4 / P; ++g) {
+          const int r = prow(g);
+          const int iv = piv(g);
+          const unsigned long long* np =
+              reinterpret_cast<const unsigned long long*>(&nodes[r][k * 4 + iv]);
+          const unsigned long long n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3];
+          const unsigned long long d0n = fma2(n1, mone, n0), d2n = fma2(n1, mone, n2),
+                                   d3n = fma2(n1, mone, n3);
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const unsigned long long u =
+                fma2(wt[q][2], d3n, fma2(wt[q][1], d2n, fma2(wt[q][0], d0n, n1)));
+            unpk2(u, ixa[g * P + q], iya[g * P + q]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          float i2[2], j2[2];
+          if constexpr (RM) {
+            RowCtx<XF> ra, rb;
+            row_setup<XF>(p, b, min(tile_y0 + prow(2 * g), p.dh - 1), ra);
+            row_setup<XF>(p, b, min(tile_y0 + prow(2 * g + 1), p.dh - 1), rb);
+            const int xa = min(tile_x0 + xloc(0), p.dw - 1);
+            const float rca = XF == EQB_EQUI2CUBE ? __ldg(p.tx + (xa - cell * p.w_face)) : 0.f;
+            coords2r<XF, true>(p, ra, rb, xa, cell, rca, i2, j2);
+          } else {
+            RowCtx<XF> rc;
+            row_setup<XF>(p, b, min(tile_y0 + prow(2 * g), p.dh - 1), rc);
+            const int xa = min(tile_x0 + xloc(2 * g), p.dw - 1);
+            const int xb = min(tile_x0 + xloc(2 * g + 1), p.dw - 1);
+            float rca = 0.f, rcb = 0.f;
+            if (XF == EQB_EQUI2CUBE) {
+              rca = __ldg(p.tx + (xa - cell * p.w_face));
+              rcb = __ldg(p.tx + (xb - cell * p.w_face));
+            }
+            coords2<XF, true>(p, rc, xa, xb, cell, rca, rcb, i2, j2);
+          }
+          ixa[2 * g] = i2[0]; ixa[2 * g + 1] = i2[1];
+          iya[2 * g] = j2[0]; iya[2 * g + 1] = j2[1];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!(ok & (1u << j))) continue;
+        const float ix = ixa[j], iy = iya[j];
+        const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
+        const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
+        const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
+        const float w_nw = __fmul_rn(ax, ay), w_ne = __fmul_rn(bx, ay);
+        const float w_sw = __fmul_rn(ax, by), w_se = __fmul_rn(bx, by);
+        const int xi = (int)xf, yi = (int)yf;
+        const int xr = xi - gx0, yr = yi - gy0;
+        const bool from_box = boxed && xr >= 0 && xr <= pitch - 2 && yr >= 0 && yr <= bh - 2;
+        T* d = d0 + poff[j];
+        float v[NC][4];
+        if (from_box) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const T* q0 = box + (c * bh + yr) * pitch + xr;
+            v[c][0] = lds_f(q0); v[c][1] = lds_f(q0 + 1);
+            v[c][2] = lds_f(q0 + pitch); v[c][3] = lds_f(q0 + pitch + 1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {  // (all loads of the pixel in flight together)
+            const T* q0 = src_b + (long long)c * p.ssc + (yi * ssh + xi);
+            if constexpr (ELT == 4) {
+              v[c][0] = ld_f(q0); v[c][1] = ld_f(q0 + 1);
+              v[c][2] = ld_f(q0 + ssh); v[c][3] = ld_f(q0 + ssh + 1);
+            } else {
+              ldg_pair<T>(q0, v[c][0], v[c][1]);
+              ldg_pair<T>(q0 + ssh, v[c][2], v[c][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const T o = OutCvt<T>::cvt(blend4(v[c][0], v[c][1], v[c][2], v[c][3], w_nw, w_ne, w_sw,
+                                            w_se), p.flags);
+          Pack<T, 1>::st(d + c * p.dsc, &o);
+        }
+      }
+    }
+    if (boxed) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + (nbox & 1u) * 8u);
+      ++nbox;
+    }
+  }
+}
+
+}  // namespace eqb
