@@ -500,7 +500,11 @@ def main():
         else:
             hin = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
             hin.copy_(src)
-            chunk = args.chunk or (4 if wl["batch"] >= 16 else 1)
+            # chunks of one frame where a frame is large (4K: 25-100 MB): the pipeline's fill
+            # and drain (one chunk each way with nothing to overlap) then cost least --
+            # measured on 32 x 4K bf16: chunk 1 / 2 / 4 / 8 = 7.64 / 7.49 / 6.84 / 6.12 Gpix/s
+            frame_bytes = c * h * w * ELT[wl["dtype"]]
+            chunk = args.chunk or (1 if frame_bytes >= (8 << 20) else 4)
             pipe = HostPipeline(op, chunk=chunk, device=dev)
             how = (f"pinned host -> equilib_b200.pipeline.HostPipeline({wl['transform']}, "
                    f"chunk={chunk}, depth=3): H2D | remap | D2H on three streams -> pinned host; "
