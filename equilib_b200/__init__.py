@@ -9,6 +9,7 @@ never called and there is no CPU fallback.
 
 from .cube2equi import Cube2Equi, cube2equi
 from .equi2cube import Equi2Cube, equi2cube
+from .equi2cube2equi import Equi2Cube2Equi, equi2cube2equi
 from .equi2equi import Equi2Equi, equi2equi
 from .equi2pers import Equi2Pers, equi2pers, get_bounding_fov
 from .grid_sample import grid_sample
@@ -31,4 +32,6 @@ __all__ = [
     "grid_sample",
     "get_bounding_fov",
     "StaticRemap",
+    "Equi2Cube2Equi",
+    "equi2cube2equi",
 ]

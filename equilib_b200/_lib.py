@@ -91,6 +91,7 @@ EXPORTS = {
     "eqb_last_error": (C.c_char_p, []),
     "eqb_remap": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p]),
     "eqb_remap_supports_channels_last": (C.c_int32, [C.POINTER(RemapDesc)]),
+    "eqb_equi2cube2equi": (C.c_int32, [C.POINTER(RemapDesc), C.POINTER(RemapDesc), C.c_void_p]),
     "eqb_remap_coords": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p, C.c_void_p]),
     "eqb_map_build": (C.c_int32, [C.POINTER(RemapDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

@@ -242,3 +242,33 @@ def remap_mapped(src: Tensor, out: Tensor, map_t: Tensor, heads_t: Tensor, mats,
                                         C.c_void_p(heads_t.data_ptr()), C.c_void_p(stream)),
             "eqb_remap_mapped",
         )
+
+
+def cube_chain(equi: Tensor, out: Tensor, mats: Tensor, rng: Tensor, tab_x: Tensor, tab_y: Tensor,
+               itab_x: Tensor, mode: int, flags: int, w_face: int) -> None:
+    """eqb_equi2cube2equi: ``out`` <- cube2equi(equi2cube(``equi``)) in one launch; the two
+    descriptors are exactly those of the two eqb_remap launches it replaces."""
+    _require_cuda(equi, "equi")
+    _require_cuda(out, "out")
+    if out.device != equi.device or out.dtype != equi.dtype:
+        raise _lib.EquilibB200Error("equi and out must share device and dtype")
+    dev = equi.device
+    for t, n in ((mats, "mats"), (rng, "rng"), (tab_x, "tab_x"), (tab_y, "tab_y"),
+                 (itab_x, "itab_x")):
+        if t.device != dev or not t.is_contiguous():
+            raise _lib.EquilibB200Error(f"{n} must be contiguous and on {dev}")
+    b, c, h, w = equi.shape
+    cells = [f * w_face for f in range(6)] + [0] * 6
+    to_cube = _fill_desc(equi, None, mats, rng, None, None, None, None, _lib.EQUI2CUBE, mode,
+                         flags, b, c, h, w, w_face, 6 * w_face, equi.stride()[:3], (0, 0, 0), 0,
+                         w_face, 6, cells, None)
+    to_equi = _fill_desc(None, out, None, tab_x, tab_y, itab_x, None, None, _lib.CUBE2EQUI, mode,
+                         flags, b, c, w_face, 6 * w_face, out.shape[2], out.shape[3], (0, 0, 0),
+                         out.stride()[:3], 0, w_face, 6, cells, None)
+    to_equi.dtype = to_cube.dtype
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(
+            _lib.lib().eqb_equi2cube2equi(C.byref(to_cube), C.byref(to_equi), C.c_void_p(stream)),
+            "eqb_equi2cube2equi",
+        )

@@ -445,15 +445,18 @@ static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
   p.use_tma = 1;
 }
 
-// The strip-node kernel (remap_lean2.cuh): bilinear, planar 1 / 3 / 4 channels, no clamp,
-// equi2equi / equi2pers / equi2cube, TMA.  fp32 images run it with the exact chain on every
+// The strip-node kernel (remap_lean2.cuh): planar 1 / 3 / 4 channels, equi2equi / equi2pers /
+// equi2cube, TMA.  Bilinear without a clamp: fp32 images run it with the exact chain on every
 // pixel unless EQB_FLAG_FAST_COORDS is set; 8/16-bit images interpolate between the strip's
-// nodes unless EQB_FLAG_EXACT_COORDS is set.
+// nodes unless EQB_FLAG_EXACT_COORDS is set.  Bicubic (every dtype, with or without a clamp):
+// the exact chain unless EQB_FLAG_FAST_COORDS is set.
 static bool can_lean2(const eqb_remap_desc* d) {
   if (d->flags & (EQB_FLAG_NO_STAGE | EQB_FLAG_NO_TMA | EQB_FLAG_NO_LEAN | EQB_FLAG_NO_LEAN2 |
                   EQB_FLAG_CHANNELS_LAST))
     return false;
-  if (d->transform > EQB_EQUI2CUBE || d->mode != EQB_BILINEAR || d->clip) return false;
+  if (d->transform > EQB_EQUI2CUBE) return false;
+  const bool cubic = d->mode == EQB_BICUBIC;
+  if (!cubic && (d->mode != EQB_BILINEAR || d->clip)) return false;
   if (d->channels != 1 && d->channels != 3 && d->channels != 4) return false;
   if (!encode_tiled()) return false;
   const long long elt = (long long)elt_size(d->dtype), per16 = 16 / elt;
@@ -462,9 +465,9 @@ static bool can_lean2(const eqb_remap_desc* d) {
   if (d->src_w > 65536 || d->src_h > 65536 || d->src_w < 16 || d->src_h < 16) return false;
   if (elt == 1) {
     // measured (gpurun_out/check_lean2.log): 2-byte stores of pixel pairs make the strip-node
-    // kernel slower than the round-1 lean kernel on uint8 (1.71 vs 1.40 ms on the bench
-    // rotations); uint8 stays there unless asked for (EQB_FLAG_FORCE_LEAN2, experiments)
-    if (!(d->flags & EQB_FLAG_FORCE_LEAN2)) return false;
+    // kernel slower than the round-1 lean kernel on uint8 BILINEAR (1.71 vs 1.40 ms on the bench
+    // rotations); it stays there unless asked for (EQB_FLAG_FORCE_LEAN2, experiments)
+    if (!cubic && !(d->flags & EQB_FLAG_FORCE_LEAN2)) return false;
     if (reinterpret_cast<uintptr_t>(d->dst) % 2) return false;
     if (d->dst_stride_b % 2 || d->dst_stride_c % 2 || d->dst_stride_h % 2) return false;
   }
@@ -515,8 +518,9 @@ template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int 
     setup_tma_l2(d, p);
     if (p.use_tma) {
       const bool exact = (d->flags & EQB_FLAG_EXACT_COORDS) ||
-                         (d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS));
-      return launch_lean2<XF>(p, d->dtype, exact, s);
+                         ((d->dtype == EQB_F32 || d->mode == EQB_BICUBIC) &&
+                          !(d->flags & EQB_FLAG_FAST_COORDS));
+      return launch_lean2<XF>(p, d->dtype, exact, d->mode, s);
     }
   }
   if (d->flags & EQB_FLAG_CHANNELS_LAST) {
@@ -756,6 +760,48 @@ int32_t eqb_remap_mapped(const eqb_remap_desc* d, const void* map, const void* h
   const cudaError_t e = launch_mapped(p, d->dtype, map, heads, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess)
     return fail(EQB_ERR_CUDA, "mapped remap launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1);
+  g_err[0] = 0;
+  return EQB_OK;
+}
+
+int32_t eqb_equi2cube2equi(const eqb_remap_desc* to_cube, const eqb_remap_desc* to_equi,
+                           void* stream) {
+  if (!to_cube || !to_equi) return fail(EQB_ERR_INVALID, "null descriptor");
+  if (to_cube->transform != EQB_EQUI2CUBE || to_equi->transform != EQB_CUBE2EQUI)
+    return fail(EQB_ERR_INVALID, "descriptors must be EQUI2CUBE followed by CUBE2EQUI");
+  Params pe, pc;
+  int rc = fill(to_cube, false, pe);
+  if (rc != EQB_OK) return rc;
+  rc = fill(to_equi, false, pc);
+  if (rc != EQB_OK) return rc;
+  const eqb_remap_desc *a = to_cube, *b = to_equi;
+  if (a->mode != b->mode || a->dtype != b->dtype || a->batch != b->batch ||
+      a->channels != b->channels || a->w_face != b->w_face)
+    return fail(EQB_ERR_INVALID, "the two stages differ in mode, dtype, batch, channels or w_face");
+  if (a->mode != EQB_NEAREST && a->mode != EQB_BILINEAR)
+    return fail(EQB_ERR_UNSUPPORTED, "fused cube chain: nearest and bilinear");
+  if (a->clip || b->clip)
+    return fail(EQB_ERR_UNSUPPORTED, "fused cube chain: no clamp (run the two launches)");
+  if (!elt_size(a->dtype)) return fail(EQB_ERR_INVALID, "unknown dtype %d", a->dtype);
+  if (a->channels <= 0 || a->channels > 4)
+    return fail(EQB_ERR_UNSUPPORTED, "fused cube chain: 1 to 4 channels");
+  if (!a->src || !b->dst) return fail(EQB_ERR_INVALID, "source / destination is null");
+  if (a->src_stride_h < a->src_w) return fail(EQB_ERR_INVALID, "src_stride_h smaller than a row");
+  if ((long long)a->src_stride_h * a->src_h >= (1ll << 31))
+    return fail(EQB_ERR_UNSUPPORTED, "a source plane spans more than 2^31 elements");
+  pe.src = a->src;
+  pe.ssb = a->src_stride_b;
+  pe.ssc = a->src_stride_c;
+  pe.ssh = a->src_stride_h;
+  pc.dst = b->dst;
+  pc.dsb = b->dst_stride_b;
+  pc.dsc = b->dst_stride_c;
+  pc.dsh = b->dst_stride_h;
+  const cudaError_t e =
+      launch_chain(pe, pc, a->mode, a->dtype, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess)
+    return fail(EQB_ERR_CUDA, "fused cube chain launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1);
   g_err[0] = 0;
   return EQB_OK;

@@ -182,7 +182,7 @@ cudaError_t launch_nhwc<EQB_XF>(const Params& p, cudaStream_t stream) {
 
 // ---- remap_lean2_kernel (remap_lean2.cuh) ---------------------------------------------------
 #if EQB_XF <= 2
-template <int XF, typename T, int NC, bool EXACT>
+template <int XF, typename T, int NC, bool EXACT, int MODE>
 static cudaError_t launch_lean2_one(Params p, cudaStream_t stream) {
   const long long tiles_x = (p.dw + kL2TileW - 1) / kL2TileW;
   const long long tiles_y = (p.dh + kL2TileH - 1) / kL2TileH;
@@ -195,34 +195,43 @@ static cudaError_t launch_lean2_one(Params p, cudaStream_t stream) {
     while (iters > 1 && p.w_face % (iters * kL2TileW)) iters >>= 1;
   p.iters = iters;
   const dim3 grid((unsigned)((tiles_x + iters - 1) / iters), (unsigned)tiles_y, (unsigned)p.B);
-  remap_lean2_kernel<XF, T, NC, EXACT>
-      <<<grid, kL2Warps * 32, 2 * l2_buf_bytes((int)sizeof(T)), stream>>>(p);
+  // (+16: the bicubic tap rows are read as aligned words that may end past the last tap)
+  remap_lean2_kernel<XF, T, NC, EXACT, MODE>
+      <<<grid, kL2Warps * 32, 2 * l2_buf_bytes((int)sizeof(T)) + 16, stream>>>(p);
   return cudaGetLastError();
 }
 
-template <int XF, typename T>
+template <int XF, typename T, int MODE>
 static cudaError_t launch_lean2_t(const Params& p, bool exact, cudaStream_t stream) {
   switch (p.C * 2 + (exact ? 1 : 0)) {
-    case 2: return launch_lean2_one<XF, T, 1, false>(p, stream);
-    case 3: return launch_lean2_one<XF, T, 1, true>(p, stream);
-    case 6: return launch_lean2_one<XF, T, 3, false>(p, stream);
-    case 7: return launch_lean2_one<XF, T, 3, true>(p, stream);
-    case 8: return launch_lean2_one<XF, T, 4, false>(p, stream);
-    case 9: return launch_lean2_one<XF, T, 4, true>(p, stream);
+    case 2: return launch_lean2_one<XF, T, 1, false, MODE>(p, stream);
+    case 3: return launch_lean2_one<XF, T, 1, true, MODE>(p, stream);
+    case 6: return launch_lean2_one<XF, T, 3, false, MODE>(p, stream);
+    case 7: return launch_lean2_one<XF, T, 3, true, MODE>(p, stream);
+    case 8: return launch_lean2_one<XF, T, 4, false, MODE>(p, stream);
+    case 9: return launch_lean2_one<XF, T, 4, true, MODE>(p, stream);
   }
   return cudaErrorNotSupported;  // (capi.cu::can_lean2)
+}
+
+template <int XF, int MODE>
+static cudaError_t launch_lean2_m(const Params& p, int dtype, bool exact, cudaStream_t stream) {
+  switch (dtype) {
+    case EQB_U8: return launch_lean2_t<XF, uint8_t, MODE>(p, exact, stream);
+    case EQB_F16: return launch_lean2_t<XF, __half, MODE>(p, exact, stream);
+    case EQB_BF16: return launch_lean2_t<XF, __nv_bfloat16, MODE>(p, exact, stream);
+    case EQB_F32: return launch_lean2_t<XF, float, MODE>(p, exact, stream);
+  }
+  return cudaErrorNotSupported;
 }
 #endif
 
 template <>
-cudaError_t launch_lean2<EQB_XF>(const Params& p, int dtype, bool exact, cudaStream_t stream) {
+cudaError_t launch_lean2<EQB_XF>(const Params& p, int dtype, bool exact, int mode,
+                                 cudaStream_t stream) {
 #if EQB_XF <= 2
-  switch (dtype) {
-    case EQB_U8: return launch_lean2_t<EQB_XF, uint8_t>(p, exact, stream);
-    case EQB_F16: return launch_lean2_t<EQB_XF, __half>(p, exact, stream);
-    case EQB_BF16: return launch_lean2_t<EQB_XF, __nv_bfloat16>(p, exact, stream);
-    case EQB_F32: return launch_lean2_t<EQB_XF, float>(p, exact, stream);
-  }
+  if (mode == EQB_BICUBIC) return launch_lean2_m<EQB_XF, EQB_BICUBIC>(p, dtype, exact, stream);
+  if (mode == EQB_BILINEAR) return launch_lean2_m<EQB_XF, EQB_BILINEAR>(p, dtype, exact, stream);
 #endif
   return cudaErrorNotSupported;
 }

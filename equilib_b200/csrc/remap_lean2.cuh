@@ -324,10 +324,151 @@ __device__ __forceinline__ void l2_blend(const L2Px (&q)[4], const float (&fx)[4
   if constexpr (NC > 3) l2_blend_channel<T, M, NC, 3>(q, w_nw, w_ne, w_sw, w_se, d0, d1, dsc, row1);
 }
 
-template <int XF, typename T, int NC, bool EXACT>
-__global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 5 ? l2_ctas(4) : 5) : (EXACT ? 5 : 7))
+
+// ---- bicubic (MODE == EQB_BICUBIC) ----------------------------------------------------------
+// The 4 x 4 taps of a pixel come from the same box (hull of the node taps widened by one pixel
+// to the left / top and two to the right / bottom); tiles within two pixels of the source
+// border -- where ATen reflects taps -- take the general path.  Arithmetic and order are those
+// of sample<..., Taps<EQB_BICUBIC>> (rows first, then columns; A = -0.75), two pixels per packed
+// instruction, so every kernel of the library produces the same bits
+// (test_staged_and_direct_kernels_agree).
+
+// cubic_coeffs() for two pixels at once (t + 1 and 1 - t as x * 1 + 1 / x * -1 + 1: the same
+// single rounding as the scalar add / subtract)
+__device__ __forceinline__ void cubic_coeffs2(unsigned long long t, unsigned long long (&c)[4]) {
+  const float A = -0.75f;
+  const unsigned long long one = bc2(1.0f);
+  unsigned long long x = fma2(t, one, one);
+  c[0] = fma2(fma2(fma2(bc2(A), x, bc2(-5.0f * A)), x, bc2(8.0f * A)), x, bc2(-4.0f * A));
+  c[1] = fma2(mul2(fma2(bc2(A + 2.0f), t, bc2(-(A + 3.0f))), t), t, one);
+  x = fma2(t, bc2(-1.0f), one);
+  c[2] = fma2(mul2(fma2(bc2(A + 2.0f), x, bc2(-(A + 3.0f))), x), x, one);
+  x = fma2(x, one, one);
+  c[3] = fma2(fma2(fma2(bc2(A), x, bc2(-5.0f * A)), x, bc2(8.0f * A)), x, bc2(-4.0f * A));
+}
+
+// Four horizontally adjacent taps starting at byte address `a` (+ compile-time OFF) of the box.
+// 1- and 2-byte pixels: the aligned 32-bit words that hold them (`aw` = a & ~3: lanes sharing a
+// word broadcast) and one or two funnel shifts by `sh` bits.
+template <typename T, int OFF>
+__device__ __forceinline__ void l2_taps4(unsigned aw, unsigned sh, float (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[0]) : "r"(aw), "n"(OFF));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[1]) : "r"(aw), "n"(OFF + 4));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[2]) : "r"(aw), "n"(OFF + 8));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[3]) : "r"(aw), "n"(OFF + 12));
+  } else if constexpr (sizeof(T) == 2) {
+    unsigned w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w0) : "r"(aw), "n"(OFF));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w1) : "r"(aw), "n"(OFF + 4));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w2) : "r"(aw), "n"(OFF + 8));
+    const unsigned x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+    if constexpr (cuda::std::is_same<T, __half>::value) {
+      const __half2 h0 = *reinterpret_cast<const __half2*>(&x0);
+      const __half2 h1 = *reinterpret_cast<const __half2*>(&x1);
+      v[0] = __low2float(h0); v[1] = __high2float(h0);
+      v[2] = __low2float(h1); v[3] = __high2float(h1);
+    } else {
+      v[0] = __uint_as_float(x0 << 16); v[1] = __uint_as_float(x0 & 0xffff0000u);
+      v[2] = __uint_as_float(x1 << 16); v[3] = __uint_as_float(x1 & 0xffff0000u);
+    }
+  } else {
+    unsigned w0, w1;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w0) : "r"(aw), "n"(OFF));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w1) : "r"(aw), "n"(OFF + 4));
+    const unsigned x = __funnelshift_r(w0, w1, sh);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = __fsub_rn(__uint_as_float(__byte_perm(x, 0x4B000000u, 0x7540u | i)), 8388608.0f);
+  }
+}
+
+// Two results of one channel: the lane's two pixels of ONE row (2- and 4-byte types: d[0] and
+// d[16]; uint8: the adjacent pair d[0..1]), clamped, converted like OutCvt.
+template <typename T>
+__device__ __forceinline__ void l2_store_pair(T* d, float o0, float o1, bool clip, float lo,
+                                              float hi, unsigned flags) {
+  if (clip) {
+    o0 = fminf(fmaxf(o0, lo), hi);
+    o1 = fminf(fmaxf(o1, lo), hi);
+  }
+  const T t0 = OutCvt<T>::cvt(o0, flags), t1 = OutCvt<T>::cvt(o1, flags);
+  if constexpr (sizeof(T) == 1) {
+    const T t[2] = {t0, t1};
+    Pack<T, 2>::st(d, t);
+  } else {
+    Pack<T, 1>::st(d, &t0);
+    Pack<T, 1>::st(d + 16, &t1);
+  }
+}
+
+// One channel of a pixel pair (x, y) from box M: 2 x 16 taps, rows then columns.
+template <typename T, int M, int NC, int CI>
+__device__ __forceinline__ void l2_bicubic_channel(unsigned ax, unsigned shx, unsigned ay,
+                                                   unsigned shy,
+                                                   const unsigned long long (&cx)[4],
+                                                   const unsigned long long (&cy)[4], float& ox,
+                                                   float& oy) {
+  constexpr int ELT = (int)sizeof(T);
+  constexpr int ROW = l2_box_w(ELT, M) * ELT;
+  constexpr int CH = CI * ROW * l2_box_h(ELT, NC, M);
+  unsigned long long acc = 0ull;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float vx[4], vy[4];
+    if (j == 0) { l2_taps4<T, CH>(ax, shx, vx); l2_taps4<T, CH>(ay, shy, vy); }
+    if (j == 1) { l2_taps4<T, CH + ROW>(ax, shx, vx); l2_taps4<T, CH + ROW>(ay, shy, vy); }
+    if (j == 2) { l2_taps4<T, CH + 2 * ROW>(ax, shx, vx); l2_taps4<T, CH + 2 * ROW>(ay, shy, vy); }
+    if (j == 3) { l2_taps4<T, CH + 3 * ROW>(ax, shx, vx); l2_taps4<T, CH + 3 * ROW>(ay, shy, vy); }
+    unsigned long long r = mul2(pk2(vx[0], vy[0]), cx[0]);
+    r = fma2(pk2(vx[1], vy[1]), cx[1], r);
+    r = fma2(pk2(vx[2], vy[2]), cx[2], r);
+    r = fma2(pk2(vx[3], vy[3]), cx[3], r);
+    acc = j == 0 ? mul2(r, cy[0]) : fma2(r, cy[j], acc);
+  }
+  unpk2(acc, ox, oy);
+}
+
+// The lane's pixel pair of one row (pixels x, y; top-left taps at byte addresses ax, ay of
+// channel 0) from box M, every channel.
+template <typename T, int M, int NC>
+__device__ __forceinline__ void l2_bicubic_pair(unsigned ax, unsigned ay, float fxx, float fxy,
+                                                float fyx, float fyy, T* d, long long dsc,
+                                                bool clip, float lo, float hi, unsigned flags) {
+  unsigned long long cx[4], cy[4];
+  cubic_coeffs2(pk2(fxx, fxy), cx);
+  cubic_coeffs2(pk2(fyx, fyy), cy);
+  constexpr unsigned MASK = sizeof(T) == 4 ? 0u : 3u;
+  const unsigned shx = (ax & MASK) * 8u, shy = (ay & MASK) * 8u;
+  ax &= ~MASK;
+  ay &= ~MASK;
+  float ox, oy;
+  l2_bicubic_channel<T, M, NC, 0>(ax, shx, ay, shy, cx, cy, ox, oy);
+  l2_store_pair<T>(d, ox, oy, clip, lo, hi, flags);
+  if constexpr (NC > 1) {
+    l2_bicubic_channel<T, M, NC, 1>(ax, shx, ay, shy, cx, cy, ox, oy);
+    l2_store_pair<T>(d + dsc, ox, oy, clip, lo, hi, flags);
+  }
+  if constexpr (NC > 2) {
+    l2_bicubic_channel<T, M, NC, 2>(ax, shx, ay, shy, cx, cy, ox, oy);
+    l2_store_pair<T>(d + 2 * dsc, ox, oy, clip, lo, hi, flags);
+  }
+  if constexpr (NC > 3) {
+    l2_bicubic_channel<T, M, NC, 3>(ax, shx, ay, shy, cx, cy, ox, oy);
+    l2_store_pair<T>(d + 3 * dsc, ox, oy, clip, lo, hi, flags);
+  }
+}
+
+template <int XF, typename T, int NC, bool EXACT, int MODE>
+__global__ void __launch_bounds__(kL2Warps * 32,
+                                  MODE == EQB_BICUBIC ? (sizeof(T) == 4 && l2_ctas(4) < 5 ? l2_ctas(4) : 5)
+                                  : sizeof(T) == 4    ? (l2_ctas(4) < 5 ? l2_ctas(4) : 5)
+                                                      : (EXACT ? 5 : 7))
     remap_lean2_kernel(const __grid_constant__ Params p) {
   constexpr int ELT = (int)sizeof(T);
+  constexpr bool CUBIC = MODE == EQB_BICUBIC;
+  // taps of a pixel span [x - LO, x + HI] x [y - LO, y + HI] around its floored coordinate
+  constexpr int LO = CUBIC ? 1 : 0, HI = CUBIC ? 2 : 1;
   constexpr int PER16 = 16 / ELT;
   constexpr int P = ELT == 1 ? 2 : 1;  // adjacent pixels per lane and row: a group is >= 2 bytes
   constexpr int BUF = l2_buf_bytes(ELT);
@@ -433,7 +574,9 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
       }
       if (__all_sync(0xffffffffu, ok)) flags |= L2_SMOOTH;
       if (straddle) flags |= L2_STRADDLE;
-      if (umin < 1.0f || umax > p.swm1f - 2.0f || vmin < 1.0f || vmax > p.shm1f - 2.0f)
+      // (bicubic: a tap within LO / HI pixels of the source border would be reflected)
+      constexpr float BM = CUBIC ? 2.0f : 1.0f;
+      if (umin < BM || umax > p.swm1f - (BM + 1.0f) || vmin < BM || vmax > p.shm1f - (BM + 1.0f))
         flags |= L2_BORDER;
       // box: top-left taps of the hull (with the footprint shift at the last column / row),
       // one more pixel right and down, margin 2
@@ -441,9 +584,9 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
       const int bx1 = (int)fminf(floorf(fminf(umax, p.swm1f)), p.swm1f - 1.0f);
       const int by0 = (int)fminf(floorf(fminf(vmin, p.shm1f)), p.shm1f - 1.0f);
       const int by1 = (int)fminf(floorf(fminf(vmax, p.shm1f)), p.shm1f - 1.0f);
-      const int gx0 = (bx0 - 2) & ~(PER16 - 1);  // 16-byte aligned (TMA requirement)
-      const int gy0 = by0 - 2;
-      const int need_w = bx1 + 4 - gx0, need_h = by1 + 4 - gy0;
+      const int gx0 = (bx0 - 2 - LO) & ~(PER16 - 1);  // 16-byte aligned (TMA requirement)
+      const int gy0 = by0 - 2 - LO;
+      const int need_w = bx1 + 3 + HI - gx0, need_h = by1 + 3 + HI - gy0;
       const unsigned fit = __ballot_sync(
           0xffffffffu, need_w <= (my_box & 0xffff) && need_h <= (my_box >> 16));
       const int m = (box_straddle || !p.use_tma) ? -1 : __ffs(fit) - 1;
@@ -473,6 +616,11 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
 #pragma unroll
     for (int j = 0; j < 3; ++j) wt[q][j] = pk2(g_l2_weights.w[t][j], g_l2_weights.w[t][j]);
   }
+
+  // bicubic: the clamp of clip_output (the bilinear launches of this kernel carry none)
+  const bool clip = CUBIC && p.clip != nullptr;
+  float clip_lo = 0.f, clip_hi = 0.f;
+  if (clip) { clip_lo = __ldg(p.clip); clip_hi = __ldg(p.clip + 1); }
 
   // The box of boxed tile n lives in buffer n & 1; phase parity of its barriers (n >> 1) & 1.
   // Thread 0 requests the box of the NEXT boxed tile while the current one is blended.
@@ -514,7 +662,8 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
       continue;
     }
 
-    const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED)) == L2_SMOOTH
+    const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED | (CUBIC ? L2_BORDER : 0))) ==
+                                            L2_SMOOTH
                                       : (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE |
                                                   L2_RAGGED)) == L2_SMOOTH);
     if (fast) {
@@ -558,23 +707,27 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
         }
       }
       L2Px px[4];
+      unsigned pa[4];  // bicubic: byte address of the top-left tap (x - 1, y - 1), channel 0
       float fx[4], fy[4];
       {
         const int pitch = p.tma_bw[m];
         const float pitchf = (float)pitch;
         // byte address = ((yf - gy0) * pitch + (xf - gx0)) * ELT + buffer; yf * pitch + xf is
         // an exact integer below 2^24
-        const int base = (int)(tile_s + (nbox & 1u) * BUF) - (gy0 * pitch + gx0) * ELT;
+        const int base =
+            (int)(tile_s + (nbox & 1u) * BUF) - ((gy0 + LO) * pitch + gx0 + LO) * ELT;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float xf = floorf(ixa[j]), yf = floorf(iya[j]);
-          if (EXACT) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
+          if (EXACT && !CUBIC) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
             xf = fminf(xf, p.swm1f - 1.0f);
             yf = fminf(yf, p.shm1f - 1.0f);
           }
           fx[j] = __fsub_rn(ixa[j], xf);
           fy[j] = __fsub_rn(iya[j], yf);
-          l2_px_setup<T>((unsigned)((int)fmaf(yf, pitchf, xf) * ELT + base), px[j]);
+          const unsigned a = (unsigned)((int)fmaf(yf, pitchf, xf) * ELT + base);
+          if constexpr (CUBIC) pa[j] = a;
+          else l2_px_setup<T>(a, px[j]);
         }
       }
       // request the next box, then wait for this one
@@ -587,7 +740,15 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
       if (row0_ok) {
         auto blend_m = [&](auto mc) {
           constexpr int M = decltype(mc)::value;
-          l2_blend<T, M, NC>(px, fx, fy, d0, d1, p.dsc, row1_ok);
+          if constexpr (CUBIC) {
+            l2_bicubic_pair<T, M, NC>(pa[0], pa[1], fx[0], fx[1], fy[0], fy[1], d0, p.dsc, clip,
+                                      clip_lo, clip_hi, p.flags);
+            if (row1_ok)
+              l2_bicubic_pair<T, M, NC>(pa[2], pa[3], fx[2], fx[3], fy[2], fy[3], d1, p.dsc, clip,
+                                        clip_lo, clip_hi, p.flags);
+          } else {
+            l2_blend<T, M, NC>(px, fx, fy, d0, d1, p.dsc, row1_ok);
+          }
         };
         switch (m) {
           case 0: blend_m(cuda::std::integral_constant<int, 0>{}); break;
@@ -669,6 +830,48 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
         const int yq = y0q + 2 * (j >> 1), x = tile_x0 + xloc(j);
         if (yq >= p.dh || x >= p.dw) continue;
         const float ix = ixa[j], iy = iya[j];
+        T* d = ((j >> 1) ? d1 : d0) + (xloc(j) - lx * P);
+        if constexpr (CUBIC) {
+          // 4 x 4 taps from the box where all of them lie inside it and none is reflected,
+          // else from global memory, each tap reflected about 0 and size-1 like ATen
+          const float xf = floorf(ix), yf = floorf(iy);
+          float cx[4], cy[4];
+          cubic_coeffs(__fsub_rn(ix, xf), cx);
+          cubic_coeffs(__fsub_rn(iy, yf), cy);
+          const int xi = (int)xf, yi = (int)yf;
+          const int xr = xi - 1 - gx0, yr = yi - 1 - gy0;
+          const bool interior = xi >= 1 && xi + 2 <= p.sw - 1 && yi >= 1 && yi + 2 <= p.sh - 1;
+          const bool from_box = boxed && interior && xr >= 0 && xr + 3 <= pitch - 1 && yr >= 0 &&
+                                yr + 3 <= bh - 1;
+          int ox[4], oy[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ox[i] = from_box ? xr + i : reflect_clip(xi - 1 + i, p.sw);
+            oy[i] = from_box ? (yr + i) * pitch : reflect_clip(yi - 1 + i, p.sh) * ssh;
+          }
+#pragma unroll 1
+          for (int c = 0; c < NC; ++c) {
+            const T* const sb = box + c * bh * pitch;
+            const T* const gb = src_b + (long long)c * p.ssc;
+            float acc = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              float v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                v[i] = from_box ? lds_f(sb + oy[r] + ox[i]) : ld_f(gb + oy[r] + ox[i]);
+              float rs = __fmul_rn(v[0], cx[0]);
+              rs = __fmaf_rn(v[1], cx[1], rs);
+              rs = __fmaf_rn(v[2], cx[2], rs);
+              rs = __fmaf_rn(v[3], cx[3], rs);
+              acc = r == 0 ? __fmul_rn(rs, cy[0]) : __fmaf_rn(rs, cy[r], acc);
+            }
+            if (clip) acc = fminf(fmaxf(acc, clip_lo), clip_hi);
+            const T o = OutCvt<T>::cvt(acc, p.flags);
+            Pack<T, 1>::st(d + c * p.dsc, &o);
+          }
+          continue;
+        }
         const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
         const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
         const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
@@ -677,7 +880,6 @@ __global__ void __launch_bounds__(kL2Warps * 32, sizeof(T) == 4 ? (l2_ctas(4) < 
         const int xi = (int)xf, yi = (int)yf;
         const int xr = xi - gx0, yr = yi - gy0;
         const bool from_box = boxed && xr >= 0 && xr <= pitch - 2 && yr >= 0 && yr <= bh - 2;
-        T* d = ((j >> 1) ? d1 : d0) + (xloc(j) - lx * P);
         float v[NC][4];
         if (from_box) {
 #pragma unroll

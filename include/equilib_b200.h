@@ -23,6 +23,10 @@
  *                           (`native()` -> F.grid_sample) for a caller-made grid.
  *   eqb_remap_coords     <- `convert_grid` of each transform, e.g.
  *                           equilib/equi2equi/torch.py:24-42 (test/debug aid).
+ *   eqb_equi2cube2equi   <- equi2cube followed by cube2equi (the two `run()` bodies above
+ *                           and the cubemap re-formatting between them,
+ *                           equilib/equi2cube/torch.py:17-76,
+ *                           equilib/cube2equi/torch.py:15-132) in one launch.
  *   eqb_minmax           <- `torch.min(src)`, `torch.max(src)` feeding
  *                           `torch.clip`, e.g. equilib/equi2equi/torch.py:197.
  *   eqb_rotation_compose <- `R_z @ R_y @ R_x` of
@@ -204,6 +208,22 @@ int32_t eqb_map_build(const eqb_remap_desc* desc, const float* coords, void* map
                       void* stream);
 int32_t eqb_remap_mapped(const eqb_remap_desc* desc, const void* map, const void* heads,
                          void* stream);
+
+/*
+ * Fused equirect -> cubemap -> equirect: the result of eqb_remap(to_cube)
+ * followed by eqb_remap(to_equi) without the cubemap ever touching memory -- the reference
+ * writes it, re-formats it and reads it back (equilib/equi2cube/torch.py:189-251,58-76,
+ * equilib/cube2equi/torch.py:22-65,324-357).  `to_cube` is the EQUI2CUBE descriptor of the first
+ * launch (src = the equirect, mats, tab_x = rng, w_face, n_cells = 6; its dst is ignored),
+ * `to_equi` the CUBE2EQUI descriptor of the second (tables, dst = the output; its src is
+ * ignored).  Both must agree in mode (nearest or bilinear), dtype, batch, channels (<= 4) and
+ * w_face and carry no clamp.  Cube taps are resolved on the virtual horizon strip, so the
+ * reference's cross-face tap bleed (cube2equi/torch.py:228-242) is reproduced; the intermediate
+ * cube pixel is rounded to the image type like a stored cubemap; every cube pixel is produced
+ * by the exact coordinate chain.
+ */
+int32_t eqb_equi2cube2equi(const eqb_remap_desc* to_cube, const eqb_remap_desc* to_equi,
+                           void* stream);
 
 /*
  * Writes the sampling coordinates of the transform (what the reference calls

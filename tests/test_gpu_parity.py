@@ -936,3 +936,117 @@ def test_static_remap_channels_last_uint8(channels):
     ref = equilib_b200.equi2equi(img, rots, fast_coords=False)
     d = (out.int() - ref.int()).abs()
     assert int(d.max()) <= 1 and rate(float((d == 0).float().mean()), 0.99)
+
+
+# --- strip-node kernel, bicubic (round 2) ---------------------------------------------------
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16", "uint8"])
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_lean2_bicubic_equals_the_direct_kernel(dtype, channels, monkeypatch):
+    """Large bicubic launches of equi2equi / equi2pers / equi2cube take the strip-node kernel
+    (4 x 4 taps from the TMA box, tiles at the source border / poles / seam on its general
+    path).  With the exact chain (the bicubic default) it must produce the bits of the
+    direct-gather kernel: every channel count, ragged sizes, with and without the clamp."""
+    img = torch.from_numpy(cases.noise_image((2, channels, 512, 1024),
+                                             "uint8" if dtype == "uint8" else "float32", 7))
+    img = img.to(DEV)
+    if dtype not in ("uint8", "float32"):
+        img = img.to(getattr(torch, dtype))
+    rots = [{"roll": 0.3, "pitch": -0.4, "yaw": 1.1}, {"roll": 1.5, "pitch": 1.2, "yaw": -2.9}]
+
+    def run_all():
+        return [
+            equilib_b200.equi2equi(img, rots, mode="bicubic"),
+            equilib_b200.equi2equi(img, rots, mode="bicubic", clip_output=False),
+            equilib_b200.equi2equi(img, rots, mode="bicubic", height=500, width=1002),
+            equilib_b200.equi2pers(img, rots, 480, 640, 100.0, mode="bicubic"),
+            equilib_b200.equi2cube(img, rots, 256, "dice", mode="bicubic"),
+            equilib_b200.equi2cube(img, rots, 192, "horizon", mode="bicubic", clip_output=False),
+        ]
+
+    n0 = _lib.launch_count()
+    lean2 = run_all()
+    assert _lib.launch_count() > n0
+    monkeypatch.setenv("EQUILIB_B200_NO_STAGE", "1")
+    direct = run_all()
+    for i, (a, b) in enumerate(zip(lean2, direct)):
+        assert torch.equal(a, b), f"output {i}: {int((a != b).sum())} elements differ"
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "uint8", "float32"])
+def test_lean2_bicubic_interpolated_coordinates_vs_oracle(dtype):
+    """``fast_coords=True`` gives bicubic the interpolated coordinates of the strip's nodes
+    (opt-in: the bicubic default is the exact chain).  Against the oracle on the band-limited
+    image: within one code value / one ulp of the output type (fp32: 2e-3 px of coordinate
+    noise times the image gradient)."""
+    img = torch.from_numpy(cases.band_limited_image((2, 3, 512, 1024),
+                                                    "uint8" if dtype == "uint8" else "float32",
+                                                    px=96, py=64))
+    x = img if dtype in ("uint8", "float32") else img.to(getattr(torch, dtype))
+    rots = HARD_ROTS[1:3]
+    out = equilib_b200.equi2equi(x.to(DEV), rots, mode="bicubic", fast_coords=True)
+    ref = oracle.equi2equi(x, rots, mode="bicubic", flavour="cuda")
+    if dtype == "uint8":
+        d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
+        d = np.minimum(d, 256 - d)
+        assert np.mean(d <= 1) >= 0.9995 and rate(np.mean(d == 0), 0.98)
+    elif dtype == "bfloat16":
+        o, r = out.float().cpu().numpy(), ref.float().numpy()
+        assert close_except_seam(o, r, 2.0 ** -7, 0.9995)
+        assert rate(np.mean(o == r), 0.98)
+    else:
+        assert close_except_seam(out.cpu().numpy(), ref.numpy(), 2e-3, 0.9995)
+
+
+# --- fused equi -> cube -> equi (SURVEY 8f N2) ----------------------------------------------
+
+
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16", "uint8"])
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_fused_cube_chain_equals_two_launches(dtype, mode):
+    """equi2cube2equi == cube2equi(equi2cube(x)) of this package bit for bit (exact chain on
+    both sides), whatever the cube format of the two-call version, including taps that bleed
+    across faces, faces that are not multiples of 64 and single-image shape rules."""
+    img = torch.from_numpy(cases.noise_image((3, 3, 256, 512),
+                                             "uint8" if dtype == "uint8" else "float32", 11))
+    img = img.to(DEV)
+    if dtype == "bfloat16":
+        img = img.to(torch.bfloat16)
+    rots = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}, {"roll": 0.3, "pitch": -0.4, "yaw": 1.1},
+            {"roll": 1.5, "pitch": 1.2, "yaw": -2.9}]
+    for w_face, (h, w), fmt in ((128, (256, 512), "horizon"), (100, (264, 520), "dice"),
+                                (64, (128, 256), "dict")):
+        cube = equilib_b200.equi2cube(img, rots, w_face, fmt, mode=mode, fast_coords=False)
+        two = equilib_b200.cube2equi(cube, fmt, h, w, mode=mode)
+        n0 = _lib.launch_count()
+        one = equilib_b200.equi2cube2equi(img, rots, w_face, h, w, mode=mode)
+        assert _lib.launch_count() == n0 + 1
+        assert one.shape == two.shape and one.dtype == two.dtype
+        assert torch.equal(one, two), f"{fmt}: {int((one != two).sum())} elements differ"
+    # single image + dict of rotations -> (C, H, W), like the two calls
+    one = equilib_b200.equi2cube2equi(img[1], rots[1], 64, 128, 256, mode=mode)
+    cube = equilib_b200.equi2cube(img[1], rots[1], 64, "horizon", mode=mode, fast_coords=False)
+    assert torch.equal(one, equilib_b200.cube2equi(cube, "horizon", 128, 256, mode=mode))
+    # class API, z_down
+    obj = equilib_b200.Equi2Cube2Equi(64, 128, 256, z_down=True, mode=mode)
+    cube = equilib_b200.equi2cube(img, rots, 64, "horizon", z_down=True, mode=mode,
+                                  fast_coords=False)
+    assert torch.equal(obj(img, rots), equilib_b200.cube2equi(cube, "horizon", 128, 256, mode=mode))
+
+
+def test_fused_cube_chain_vs_oracle_composition():
+    """Against the oracle's own two-step composition (reference semantics end to end)."""
+    img = cases.band_limited_image((2, 3, 256, 512), "float32", px=96, py=64)
+    rots = HARD_ROTS[1:3]
+    cube = oracle.equi2cube(torch.from_numpy(img), rots, 128, "horizon", flavour="cuda")
+    ref = oracle.cube2equi(cube, "horizon", 256, 512, flavour="cuda")
+    out = equilib_b200.equi2cube2equi(torch.from_numpy(img).to(DEV), rots, 128, 256, 512)
+    assert helpers.frac_close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-5) >= 0.999
+    # bicubic and exact_clip take the two launches behind the same entry point
+    out = equilib_b200.equi2cube2equi(torch.from_numpy(img).to(DEV), rots, 128, 256, 512,
+                                      mode="bicubic")
+    cube = oracle.equi2cube(torch.from_numpy(img), rots, 128, "horizon", mode="bicubic",
+                            flavour="cuda")
+    ref = oracle.cube2equi(cube, "horizon", 256, 512, mode="bicubic", flavour="cuda")
+    assert helpers.frac_close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=5e-5) >= 0.995
