@@ -44,8 +44,8 @@ class Options:
     saturate_uint8  saturate the uint8 store instead of wrapping like the reference
     clip_group      torch.distributed group over which the clip range is all-reduced
                     (sharded batches, equilib_b200/sharded.py)
-    fast_coords     None = library default (on for uint8 / fp16 / bf16 bilinear, off for
-                    fp32); True / False force the interpolated / exact coordinate chain
+    fast_coords     None = library default (on for uint8 / fp16 / bf16 bilinear and bicubic on
+                    large launches, off for fp32); True / False force the interpolated / exact coordinate chain
     """
 
     __slots__ = ("exact_clip", "saturate_uint8", "clip_group", "fast_coords")

@@ -448,8 +448,8 @@ static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
 // The strip-node kernel (remap_lean2.cuh): planar 1 / 3 / 4 channels, equi2equi / equi2pers /
 // equi2cube, TMA.  Bilinear without a clamp: fp32 images run it with the exact chain on every
 // pixel unless EQB_FLAG_FAST_COORDS is set; 8/16-bit images interpolate between the strip's
-// nodes unless EQB_FLAG_EXACT_COORDS is set.  Bicubic (every dtype, with or without a clamp):
-// the exact chain unless EQB_FLAG_FAST_COORDS is set.
+// nodes unless EQB_FLAG_EXACT_COORDS is set.  Bicubic (with or without a clamp): the same
+// coordinate policy, every dtype including uint8.
 static bool can_lean2(const eqb_remap_desc* d) {
   if (d->flags & (EQB_FLAG_NO_STAGE | EQB_FLAG_NO_TMA | EQB_FLAG_NO_LEAN | EQB_FLAG_NO_LEAN2 |
                   EQB_FLAG_CHANNELS_LAST))
@@ -499,7 +499,8 @@ static void setup_tma_l2(const eqb_remap_desc* d, Params& p) {
     if (strides[i] == 0 || strides[i] % 16) return;
   for (int m = 0; m < 16; ++m) p.tma_bw[m] = p.tma_bh[m] = 0;
   for (int m = 0; m < kL2Boxes; ++m) {
-    const int bw = l2_box_w(elt, m), bh = l2_box_h(elt, d->channels, m);
+    const int bw = l2_box_w(elt, m);
+    const int bh = l2_box_h(elt, d->channels, m, d->mode == EQB_BICUBIC);
     if (bw > 256 || bh < kL2MinBoxH) continue;
     const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)d->channels, 1};
     if (encode_cached(&p.tmaps[m], dt, const_cast<void*>(d->src), dims, strides, box) !=
@@ -518,8 +519,7 @@ template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int 
     setup_tma_l2(d, p);
     if (p.use_tma) {
       const bool exact = (d->flags & EQB_FLAG_EXACT_COORDS) ||
-                         ((d->dtype == EQB_F32 || d->mode == EQB_BICUBIC) &&
-                          !(d->flags & EQB_FLAG_FAST_COORDS));
+                         (d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS));
       return launch_lean2<XF>(p, d->dtype, exact, d->mode, s);
     }
   }

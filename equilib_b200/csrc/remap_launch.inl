@@ -196,8 +196,12 @@ static cudaError_t launch_lean2_one(Params p, cudaStream_t stream) {
   p.iters = iters;
   const dim3 grid((unsigned)((tiles_x + iters - 1) / iters), (unsigned)tiles_y, (unsigned)p.B);
   // (+16: the bicubic tap rows are read as aligned words that may end past the last tap)
+  constexpr int SMEM = 2 * l2_buf_bytes((int)sizeof(T), MODE == EQB_BICUBIC) + 16;
+  if (SMEM > 48 * 1024)  // (the opt-in is per device: set it on every launch that needs it)
+    cudaFuncSetAttribute(remap_lean2_kernel<XF, T, NC, EXACT, MODE>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   remap_lean2_kernel<XF, T, NC, EXACT, MODE>
-      <<<grid, kL2Warps * 32, 2 * l2_buf_bytes((int)sizeof(T)) + 16, stream>>>(p);
+      <<<grid, kL2Warps * 32, SMEM, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -57,9 +57,21 @@ static_assert(kL2Boxes <= kTmaSlots, "tensor-map slots");
 #ifndef EQB_L2_BUF_KB_F32
 #define EQB_L2_BUF_KB_F32 18  // (measured 16 / 18 / 20 KB: 1.17 / 1.10 / 1.13 ms on 16 x 4K fp32, bench rotations)
 #endif
-EQB_HD constexpr int l2_buf_bytes(int elt) { return elt == 4 ? EQB_L2_BUF_KB_F32 * 1024 : 12 * 1024; }
+// (bicubic: 18 KB for every type -- its 96 registers allow 5 CTAs per SM anyway, and the 4 x 4
+// footprint of a tile is 3 pixels wider and taller: with 12 KB, 12 % of the tiles of the bench
+// rotations and 25 % on rotations drawn from SO(3) fit no box; with 18 KB 5 % / 7 %
+// (tools/sim_tiles.py))
+#ifndef EQB_L2_BUF_KB_F32_CUBIC
+#define EQB_L2_BUF_KB_F32_CUBIC 24  // (measured 18 / 24 / 32 KB: 2.75 / 2.07 / 2.11 ms on 16 x 4K fp32 bicubic, bench rotations)
+#endif
+EQB_HD constexpr int l2_buf_bytes(int elt, bool cubic = false) {
+  return (elt == 4 && cubic) ? EQB_L2_BUF_KB_F32_CUBIC * 1024
+         : (elt == 4 || cubic) ? EQB_L2_BUF_KB_F32 * 1024 : 12 * 1024;
+}
 // CTAs per SM the shared memory allows (two buffers + ~6 KB of nodes, headers, reserve)
-EQB_HD constexpr int l2_ctas(int elt) { return 227 * 1024 / (2 * l2_buf_bytes(elt) + 6 * 1024); }
+EQB_HD constexpr int l2_ctas(int elt, bool cubic = false) {
+  return 227 * 1024 / (2 * l2_buf_bytes(elt, cubic) + 6 * 1024);
+}
 
 // Box m: l2_box_w x l2_box_h source pixels x channels.  Boxes 0-1 are small (upright and
 // mildly rolled views); the others spend the whole buffer in different aspect ratios: 48
@@ -71,8 +83,8 @@ EQB_HD constexpr int l2_box_w(int elt, int m) {
   const int per16 = 16 / elt;
   return (w + per16 - 1) / per16 * per16;
 }
-EQB_HD constexpr int l2_box_h(int elt, int nc, int m) {
-  const int budget = l2_buf_bytes(elt) / elt / nc;
+EQB_HD constexpr int l2_box_h(int elt, int nc, int m, bool cubic = false) {
+  const int budget = l2_buf_bytes(elt, cubic) / elt / nc;
   const int full = budget / l2_box_w(elt, m) < 128 ? budget / l2_box_w(elt, m) : 128;
   const int small = m == 0 ? 24 : 32;
   return m < 2 && small < full ? small : full;
@@ -347,21 +359,24 @@ __device__ __forceinline__ void cubic_coeffs2(unsigned long long t, unsigned lon
   c[3] = fma2(fma2(fma2(bc2(A), x, bc2(-5.0f * A)), x, bc2(8.0f * A)), x, bc2(-4.0f * A));
 }
 
-// Four horizontally adjacent taps starting at byte address `a` (+ compile-time OFF) of the box.
-// 1- and 2-byte pixels: the aligned 32-bit words that hold them (`aw` = a & ~3: lanes sharing a
-// word broadcast) and one or two funnel shifts by `sh` bits.
-template <typename T, int OFF>
+// Four horizontally adjacent taps starting at byte address `a` of the box (the box shape is a
+// run-time value here, unlike in the bilinear blend: eleven unrolled copies of the 96-tap blend
+// were 13 k instructions, and ncu showed half of all stall samples waiting for instruction
+// fetch -- profiles/r02_experiments/ncu_lean2_bicubic_unrolled_boxes.txt).  1- and 2-byte
+// pixels: the aligned 32-bit words that hold the taps (`aw` = a & ~3: lanes sharing a word
+// broadcast) and one or two funnel shifts by `sh` bits.
+template <typename T>
 __device__ __forceinline__ void l2_taps4(unsigned aw, unsigned sh, float (&v)[4]) {
   if constexpr (sizeof(T) == 4) {
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[0]) : "r"(aw), "n"(OFF));
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[1]) : "r"(aw), "n"(OFF + 4));
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[2]) : "r"(aw), "n"(OFF + 8));
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v[3]) : "r"(aw), "n"(OFF + 12));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(aw));
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v[1]) : "r"(aw));
+    asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(v[2]) : "r"(aw));
+    asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(v[3]) : "r"(aw));
   } else if constexpr (sizeof(T) == 2) {
     unsigned w0, w1, w2;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w0) : "r"(aw), "n"(OFF));
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w1) : "r"(aw), "n"(OFF + 4));
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w2) : "r"(aw), "n"(OFF + 8));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(aw));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(aw));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(aw));
     const unsigned x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
     if constexpr (cuda::std::is_same<T, __half>::value) {
       const __half2 h0 = *reinterpret_cast<const __half2*>(&x0);
@@ -374,8 +389,8 @@ __device__ __forceinline__ void l2_taps4(unsigned aw, unsigned sh, float (&v)[4]
     }
   } else {
     unsigned w0, w1;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w0) : "r"(aw), "n"(OFF));
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w1) : "r"(aw), "n"(OFF + 4));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(aw));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(aw));
     const unsigned x = __funnelshift_r(w0, w1, sh);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -402,24 +417,20 @@ __device__ __forceinline__ void l2_store_pair(T* d, float o0, float o1, bool cli
   }
 }
 
-// One channel of a pixel pair (x, y) from box M: 2 x 16 taps, rows then columns.
-template <typename T, int M, int NC, int CI>
+// One channel of a pixel pair (x, y): 2 x 16 taps from the box rows at ax / ay + j * row bytes,
+// rows then columns.
+template <typename T>
 __device__ __forceinline__ void l2_bicubic_channel(unsigned ax, unsigned shx, unsigned ay,
-                                                   unsigned shy,
+                                                   unsigned shy, unsigned row,
                                                    const unsigned long long (&cx)[4],
                                                    const unsigned long long (&cy)[4], float& ox,
                                                    float& oy) {
-  constexpr int ELT = (int)sizeof(T);
-  constexpr int ROW = l2_box_w(ELT, M) * ELT;
-  constexpr int CH = CI * ROW * l2_box_h(ELT, NC, M);
   unsigned long long acc = 0ull;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float vx[4], vy[4];
-    if (j == 0) { l2_taps4<T, CH>(ax, shx, vx); l2_taps4<T, CH>(ay, shy, vy); }
-    if (j == 1) { l2_taps4<T, CH + ROW>(ax, shx, vx); l2_taps4<T, CH + ROW>(ay, shy, vy); }
-    if (j == 2) { l2_taps4<T, CH + 2 * ROW>(ax, shx, vx); l2_taps4<T, CH + 2 * ROW>(ay, shy, vy); }
-    if (j == 3) { l2_taps4<T, CH + 3 * ROW>(ax, shx, vx); l2_taps4<T, CH + 3 * ROW>(ay, shy, vy); }
+    l2_taps4<T>(ax + j * row, shx, vx);
+    l2_taps4<T>(ay + j * row, shy, vy);
     unsigned long long r = mul2(pk2(vx[0], vy[0]), cx[0]);
     r = fma2(pk2(vx[1], vy[1]), cx[1], r);
     r = fma2(pk2(vx[2], vy[2]), cx[2], r);
@@ -430,11 +441,12 @@ __device__ __forceinline__ void l2_bicubic_channel(unsigned ax, unsigned shx, un
 }
 
 // The lane's pixel pair of one row (pixels x, y; top-left taps at byte addresses ax, ay of
-// channel 0) from box M, every channel.
-template <typename T, int M, int NC>
+// channel 0) from a box with `row` bytes per row and `plane` bytes per channel, every channel.
+template <typename T, int NC>
 __device__ __forceinline__ void l2_bicubic_pair(unsigned ax, unsigned ay, float fxx, float fxy,
-                                                float fyx, float fyy, T* d, long long dsc,
-                                                bool clip, float lo, float hi, unsigned flags) {
+                                                float fyx, float fyy, unsigned row,
+                                                unsigned plane, T* d, long long dsc, bool clip,
+                                                float lo, float hi, unsigned flags) {
   unsigned long long cx[4], cy[4];
   cubic_coeffs2(pk2(fxx, fxy), cx);
   cubic_coeffs2(pk2(fyx, fyy), cy);
@@ -442,26 +454,73 @@ __device__ __forceinline__ void l2_bicubic_pair(unsigned ax, unsigned ay, float 
   const unsigned shx = (ax & MASK) * 8u, shy = (ay & MASK) * 8u;
   ax &= ~MASK;
   ay &= ~MASK;
-  float ox, oy;
-  l2_bicubic_channel<T, M, NC, 0>(ax, shx, ay, shy, cx, cy, ox, oy);
-  l2_store_pair<T>(d, ox, oy, clip, lo, hi, flags);
-  if constexpr (NC > 1) {
-    l2_bicubic_channel<T, M, NC, 1>(ax, shx, ay, shy, cx, cy, ox, oy);
-    l2_store_pair<T>(d + dsc, ox, oy, clip, lo, hi, flags);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float ox, oy;
+    l2_bicubic_channel<T>(ax + c * plane, shx, ay + c * plane, shy, row, cx, cy, ox, oy);
+    l2_store_pair<T>(d + c * dsc, ox, oy, clip, lo, hi, flags);
   }
-  if constexpr (NC > 2) {
-    l2_bicubic_channel<T, M, NC, 2>(ax, shx, ay, shy, cx, cy, ox, oy);
-    l2_store_pair<T>(d + 2 * dsc, ox, oy, clip, lo, hi, flags);
+}
+
+// One pixel on the general path (tiles at the source border, poles, seam; footprints that fit
+// no box): the 4 x 4 taps from the box where all of them lie inside it and none is reflected,
+// else from global memory, each tap reflected about 0 and size-1 like ATen.  One copy of the
+// code (not inlined: the general path is rare, the instruction cache is not).
+template <typename T, int NC>
+__device__ __noinline__ void l2_bicubic_general(const Params& p, float ix, float iy, bool boxed,
+                                                const T* box, int pitch, int bh, int gx0, int gy0,
+                                                const T* src_b, T* d, bool clip, float clip_lo,
+                                                float clip_hi) {
+  const int ssh = (int)p.ssh;
+  const float xf = floorf(ix), yf = floorf(iy);
+  float cx[4], cy[4];
+  cubic_coeffs(__fsub_rn(ix, xf), cx);
+  cubic_coeffs(__fsub_rn(iy, yf), cy);
+  const int xi = (int)xf, yi = (int)yf;
+  const int xr = xi - 1 - gx0, yr = yi - 1 - gy0;
+  const bool interior = xi >= 1 && xi + 2 <= p.sw - 1 && yi >= 1 && yi + 2 <= p.sh - 1;
+  const bool from_box =
+      boxed && interior && xr >= 0 && xr + 3 <= pitch - 1 && yr >= 0 && yr + 3 <= bh - 1;
+  int ox[4], oy[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ox[i] = from_box ? xr + i : reflect_clip(xi - 1 + i, p.sw);
+    oy[i] = from_box ? (yr + i) * pitch : reflect_clip(yi - 1 + i, p.sh) * ssh;
   }
-  if constexpr (NC > 3) {
-    l2_bicubic_channel<T, M, NC, 3>(ax, shx, ay, shy, cx, cy, ox, oy);
-    l2_store_pair<T>(d + 3 * dsc, ox, oy, clip, lo, hi, flags);
+#pragma unroll 1
+  for (int c = 0; c < NC; ++c) {
+    const T* const sb = box + c * bh * pitch;
+    const T* const gb = src_b + (long long)c * p.ssc;
+    float v[4][4];
+    if (from_box) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[r][i] = lds_f(sb + oy[r] + ox[i]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[r][i] = ld_f(gb + oy[r] + ox[i]);
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float rs = __fmul_rn(v[r][0], cx[0]);
+      rs = __fmaf_rn(v[r][1], cx[1], rs);
+      rs = __fmaf_rn(v[r][2], cx[2], rs);
+      rs = __fmaf_rn(v[r][3], cx[3], rs);
+      acc = r == 0 ? __fmul_rn(rs, cy[0]) : __fmaf_rn(rs, cy[r], acc);
+    }
+    if (clip) acc = fminf(fmaxf(acc, clip_lo), clip_hi);
+    const T o = OutCvt<T>::cvt(acc, p.flags);
+    Pack<T, 1>::st(d + c * p.dsc, &o);
   }
 }
 
 template <int XF, typename T, int NC, bool EXACT, int MODE>
 __global__ void __launch_bounds__(kL2Warps * 32,
-                                  MODE == EQB_BICUBIC ? (sizeof(T) == 4 && l2_ctas(4) < 5 ? l2_ctas(4) : 5)
+                                  MODE == EQB_BICUBIC ? (l2_ctas(sizeof(T), true) < 5 ? l2_ctas(sizeof(T), true) : 5)
                                   : sizeof(T) == 4    ? (l2_ctas(4) < 5 ? l2_ctas(4) : 5)
                                                       : (EXACT ? 5 : 7))
     remap_lean2_kernel(const __grid_constant__ Params p) {
@@ -471,7 +530,7 @@ __global__ void __launch_bounds__(kL2Warps * 32,
   constexpr int LO = CUBIC ? 1 : 0, HI = CUBIC ? 2 : 1;
   constexpr int PER16 = 16 / ELT;
   constexpr int P = ELT == 1 ? 2 : 1;  // adjacent pixels per lane and row: a group is >= 2 bytes
-  constexpr int BUF = l2_buf_bytes(ELT);
+  constexpr int BUF = l2_buf_bytes(ELT, MODE == EQB_BICUBIC);
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // two box buffers
   __shared__ __align__(16) float2 nodes[kL2TileH][kL2Cols + 1];  // (ui, uj)
   __shared__ __align__(16) int4 headers[kL2MaxIters];
@@ -617,6 +676,15 @@ __global__ void __launch_bounds__(kL2Warps * 32,
     for (int j = 0; j < 3; ++j) wt[q][j] = pk2(g_l2_weights.w[t][j], g_l2_weights.w[t][j]);
   }
 
+  // EXACT: the batch matrix and the row terms of the lane's two rows, loaded once per strip (in
+  // the tile loop they were 22 dependent table loads per tile in front of every chain: the
+  // fp32 kernel showed 31 % long-scoreboard stalls)
+  RowCtx<XF> rows[2];
+  if constexpr (EXACT) {
+    row_setup<XF>(p, b, min(y0q, p.dh - 1), rows[0]);
+    row_setup<XF>(p, b, min(y0q + 2, p.dh - 1), rows[1]);
+  }
+
   // bicubic: the clamp of clip_output (the bilinear launches of this kernel carry none)
   const bool clip = CUBIC && p.clip != nullptr;
   float clip_lo = 0.f, clip_hi = 0.f;
@@ -689,11 +757,9 @@ __global__ void __launch_bounds__(kL2Warps * 32,
           }
         }
       } else {
-        RowCtx<XF> rc;
 #pragma unroll
         for (int gy = 0; gy < 2; ++gy) {
-          const int y = min(y0q + 2 * gy, p.dh - 1);
-          row_setup<XF>(p, b, y, rc);
+          const RowCtx<XF>& rc = rows[gy];
           const int xa = tile_x0 + xloc(2 * gy), xb = tile_x0 + xloc(2 * gy + 1);
           float rca = 0.f, rcb = 0.f;
           if (XF == EQB_EQUI2CUBE) {
@@ -737,18 +803,20 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       }
       __syncwarp();
       mbar_wait_backoff(full_s + (nbox & 1u) * 8u, (nbox >> 1) & 1u);
-      if (row0_ok) {
+      if constexpr (CUBIC) {
+        if (row0_ok) {
+          const unsigned row = (unsigned)(p.tma_bw[m] * ELT);
+          const unsigned plane = row * (unsigned)p.tma_bh[m];
+          l2_bicubic_pair<T, NC>(pa[0], pa[1], fx[0], fx[1], fy[0], fy[1], row, plane, d0, p.dsc,
+                                 clip, clip_lo, clip_hi, p.flags);
+          if (row1_ok)
+            l2_bicubic_pair<T, NC>(pa[2], pa[3], fx[2], fx[3], fy[2], fy[3], row, plane, d1,
+                                   p.dsc, clip, clip_lo, clip_hi, p.flags);
+        }
+      } else if (row0_ok) {
         auto blend_m = [&](auto mc) {
           constexpr int M = decltype(mc)::value;
-          if constexpr (CUBIC) {
-            l2_bicubic_pair<T, M, NC>(pa[0], pa[1], fx[0], fx[1], fy[0], fy[1], d0, p.dsc, clip,
-                                      clip_lo, clip_hi, p.flags);
-            if (row1_ok)
-              l2_bicubic_pair<T, M, NC>(pa[2], pa[3], fx[2], fx[3], fy[2], fy[3], d1, p.dsc, clip,
-                                        clip_lo, clip_hi, p.flags);
-          } else {
-            l2_blend<T, M, NC>(px, fx, fy, d0, d1, p.dsc, row1_ok);
-          }
+          l2_blend<T, M, NC>(px, fx, fy, d0, d1, p.dsc, row1_ok);
         };
         switch (m) {
           case 0: blend_m(cuda::std::integral_constant<int, 0>{}); break;
@@ -832,44 +900,8 @@ __global__ void __launch_bounds__(kL2Warps * 32,
         const float ix = ixa[j], iy = iya[j];
         T* d = ((j >> 1) ? d1 : d0) + (xloc(j) - lx * P);
         if constexpr (CUBIC) {
-          // 4 x 4 taps from the box where all of them lie inside it and none is reflected,
-          // else from global memory, each tap reflected about 0 and size-1 like ATen
-          const float xf = floorf(ix), yf = floorf(iy);
-          float cx[4], cy[4];
-          cubic_coeffs(__fsub_rn(ix, xf), cx);
-          cubic_coeffs(__fsub_rn(iy, yf), cy);
-          const int xi = (int)xf, yi = (int)yf;
-          const int xr = xi - 1 - gx0, yr = yi - 1 - gy0;
-          const bool interior = xi >= 1 && xi + 2 <= p.sw - 1 && yi >= 1 && yi + 2 <= p.sh - 1;
-          const bool from_box = boxed && interior && xr >= 0 && xr + 3 <= pitch - 1 && yr >= 0 &&
-                                yr + 3 <= bh - 1;
-          int ox[4], oy[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            ox[i] = from_box ? xr + i : reflect_clip(xi - 1 + i, p.sw);
-            oy[i] = from_box ? (yr + i) * pitch : reflect_clip(yi - 1 + i, p.sh) * ssh;
-          }
-#pragma unroll 1
-          for (int c = 0; c < NC; ++c) {
-            const T* const sb = box + c * bh * pitch;
-            const T* const gb = src_b + (long long)c * p.ssc;
-            float acc = 0.0f;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              float v[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                v[i] = from_box ? lds_f(sb + oy[r] + ox[i]) : ld_f(gb + oy[r] + ox[i]);
-              float rs = __fmul_rn(v[0], cx[0]);
-              rs = __fmaf_rn(v[1], cx[1], rs);
-              rs = __fmaf_rn(v[2], cx[2], rs);
-              rs = __fmaf_rn(v[3], cx[3], rs);
-              acc = r == 0 ? __fmul_rn(rs, cy[0]) : __fmaf_rn(rs, cy[r], acc);
-            }
-            if (clip) acc = fminf(fmaxf(acc, clip_lo), clip_hi);
-            const T o = OutCvt<T>::cvt(acc, p.flags);
-            Pack<T, 1>::st(d + c * p.dsc, &o);
-          }
+          l2_bicubic_general<T, NC>(p, ix, iy, boxed, box, pitch, bh, gx0, gy0, src_b, d, clip,
+                                    clip_lo, clip_hi);
           continue;
         }
         const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);

@@ -13,9 +13,17 @@ strip before sampling -- from one kernel in which the cubemap never touches memo
 (``eqb_equi2cube2equi``, csrc/remap_chain.cu): bit-equal to this package's own two calls with
 ``fast_coords=False``.
 
-Served: nearest and bilinear, every dtype of the package, up to 4 channels, no clamp (for
-these modes ``clip_output`` cannot change a stored value beyond 2 ulp, see
-``_common.clip_tensor``; ``exact_clip=True`` and bicubic take the two launches).
+The fused kernel serves nearest and bilinear, every dtype of the package, up to 4 channels, no
+clamp (for these modes ``clip_output`` cannot change a stored value beyond 2 ulp, see
+``_common.clip_tensor``; ``exact_clip=True`` and bicubic always take the two launches).
+
+``fused=None`` (default) picks by measurement (16 x 4K frames, w_face 1024, B200,
+profiles/r02_round2b.jsonl): **nearest** runs fused -- one chain and one gather per output
+pixel, no cubemap: 1.43 ms instead of 2.00 (fp32), 1.44 instead of 1.86 (bf16), 1.48 / 1.47
+(uint8) -- while **bilinear** runs the two launches: fused, every output pixel evaluates four
+cube pixels of four source taps each (48 gathers per pixel for RGB instead of 12 + 12 staged
+ones), 5.5 ms against 2.5 (fp32) / 1.8 (bf16).  ``fused=True`` forces the single launch (no
+intermediate: 2.4 GB less memory for 16 fp32 frames), ``fused=False`` the two launches.
 """
 
 from __future__ import annotations
@@ -26,8 +34,8 @@ import torch
 
 from . import _common as K
 from . import _ops, _prep
-from . import cube2equi as _c2e
-from . import equi2cube as _e2c
+from .cube2equi import run as _cube2equi_run
+from .equi2cube import run as _equi2cube_run
 
 __all__ = ["Equi2Cube2Equi", "equi2cube2equi"]
 
@@ -58,7 +66,7 @@ class Equi2Cube2Equi(object):
 
 
 def fused_ok(equi: torch.Tensor, mode: str, clip_output: bool, opt: K.Options) -> bool:
-    """Does the one-launch chain serve this call?  (Else: the two launches.)"""
+    """Can the one-launch chain serve this call?  (Else: the two launches.)"""
     if mode not in ("nearest", "bilinear") or equi.shape[1] > 4:
         return False
     # a clamp is launched only where it can change a value (_common.clip_tensor)
@@ -79,6 +87,7 @@ def equi2cube2equi(
 ) -> torch.Tensor:
     K.require_cuda_tensor(equi, "equi")
     K.check_backend(kwargs)
+    fused = kwargs.pop("fused", None)
     opt = K.pop_options(kwargs)
     equi, rots, is_single = K.normalise_single(equi, rots)
     equi = K.check_image(equi, "equi")
@@ -88,12 +97,14 @@ def equi2cube2equi(
     K.mode_code(mode)
     # cube2equi's size rule (equilib/cube2equi/base.py:94)
     assert height % 8 == 0 and width % 8 == 0, "ERR: height and width must be multiples of 8"
-    if fused_ok(equi, mode, clip_output, opt):
+    if fused is None:
+        fused = mode == "nearest"
+    if fused and fused_ok(equi, mode, clip_output, opt):
         out = run(equi, rots, int(w_face), int(height), int(width), z_down, mode, opt)
     else:
-        cube = _e2c.run(equi, rots, w_face=w_face, cube_format="horizon", z_down=z_down,
+        cube = _equi2cube_run(equi, rots, w_face=w_face, cube_format="horizon", z_down=z_down,
                         mode=mode, clip_output=clip_output, opt=opt)
-        out = _c2e.run(cube, "horizon", height=height, width=width, mode=mode,
+        out = _cube2equi_run(cube, "horizon", height=height, width=width, mode=mode,
                        clip_output=clip_output, opt=opt)
     # cube2equi squeezes whenever the batch is 1 (equilib/cube2equi/base.py:157-158)
     if is_single or out.shape[0] == 1:

@@ -69,7 +69,8 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
                                    div / atan2 instead of their inlined fast paths   */
 #define EQB_FLAG_NO_STAGE 8u    /* never use the shared-memory staged kernel           */
 #define EQB_FLAG_EXACT_COORDS 16u /* 16/8-bit images: exact coordinate chain on every     \
-                                    pixel.  Default for these types: the chain on every    \
+                                    pixel.  Default for these types (bilinear and bicubic  \
+                                    on large launches): the chain on every                 \
                                     4th / 8th pixel of a row + cubic interpolation along  \
                                     x -- measured <= 1.7e-3 px (mean 1.8e-4 px) from the   \
                                     exact chain at 2048 x 4096, test bound 3e-3 px;        \

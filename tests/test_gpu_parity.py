@@ -946,8 +946,9 @@ def test_static_remap_channels_last_uint8(channels):
 def test_lean2_bicubic_equals_the_direct_kernel(dtype, channels, monkeypatch):
     """Large bicubic launches of equi2equi / equi2pers / equi2cube take the strip-node kernel
     (4 x 4 taps from the TMA box, tiles at the source border / poles / seam on its general
-    path).  With the exact chain (the bicubic default) it must produce the bits of the
-    direct-gather kernel: every channel count, ragged sizes, with and without the clamp."""
+    path).  With the exact chain (``fast_coords=False``; the fp32 default) it must produce the
+    bits of the direct-gather kernel: every channel count, ragged sizes, with and without the
+    clamp."""
     img = torch.from_numpy(cases.noise_image((2, channels, 512, 1024),
                                              "uint8" if dtype == "uint8" else "float32", 7))
     img = img.to(DEV)
@@ -956,13 +957,14 @@ def test_lean2_bicubic_equals_the_direct_kernel(dtype, channels, monkeypatch):
     rots = [{"roll": 0.3, "pitch": -0.4, "yaw": 1.1}, {"roll": 1.5, "pitch": 1.2, "yaw": -2.9}]
 
     def run_all():
+        kw = dict(mode="bicubic", fast_coords=False)
         return [
-            equilib_b200.equi2equi(img, rots, mode="bicubic"),
-            equilib_b200.equi2equi(img, rots, mode="bicubic", clip_output=False),
-            equilib_b200.equi2equi(img, rots, mode="bicubic", height=500, width=1002),
-            equilib_b200.equi2pers(img, rots, 480, 640, 100.0, mode="bicubic"),
-            equilib_b200.equi2cube(img, rots, 256, "dice", mode="bicubic"),
-            equilib_b200.equi2cube(img, rots, 192, "horizon", mode="bicubic", clip_output=False),
+            equilib_b200.equi2equi(img, rots, **kw),
+            equilib_b200.equi2equi(img, rots, clip_output=False, **kw),
+            equilib_b200.equi2equi(img, rots, height=500, width=1002, **kw),
+            equilib_b200.equi2pers(img, rots, 480, 640, 100.0, **kw),
+            equilib_b200.equi2cube(img, rots, 256, "dice", **kw),
+            equilib_b200.equi2cube(img, rots, 192, "horizon", clip_output=False, **kw),
         ]
 
     n0 = _lib.launch_count()
@@ -976,8 +978,8 @@ def test_lean2_bicubic_equals_the_direct_kernel(dtype, channels, monkeypatch):
 
 @pytest.mark.parametrize("dtype", ["bfloat16", "uint8", "float32"])
 def test_lean2_bicubic_interpolated_coordinates_vs_oracle(dtype):
-    """``fast_coords=True`` gives bicubic the interpolated coordinates of the strip's nodes
-    (opt-in: the bicubic default is the exact chain).  Against the oracle on the band-limited
+    """Interpolated coordinates of the strip's nodes under bicubic sampling (the default for
+    8/16-bit images, opt-in for fp32).  Against the oracle on the band-limited
     image: within one code value / one ulp of the output type (fp32: 2e-3 px of coordinate
     noise times the image gradient)."""
     img = torch.from_numpy(cases.band_limited_image((2, 3, 512, 1024),
@@ -1020,19 +1022,27 @@ def test_fused_cube_chain_equals_two_launches(dtype, mode):
         cube = equilib_b200.equi2cube(img, rots, w_face, fmt, mode=mode, fast_coords=False)
         two = equilib_b200.cube2equi(cube, fmt, h, w, mode=mode)
         n0 = _lib.launch_count()
-        one = equilib_b200.equi2cube2equi(img, rots, w_face, h, w, mode=mode)
+        one = equilib_b200.equi2cube2equi(img, rots, w_face, h, w, mode=mode, fused=True)
         assert _lib.launch_count() == n0 + 1
         assert one.shape == two.shape and one.dtype == two.dtype
         assert torch.equal(one, two), f"{fmt}: {int((one != two).sum())} elements differ"
     # single image + dict of rotations -> (C, H, W), like the two calls
-    one = equilib_b200.equi2cube2equi(img[1], rots[1], 64, 128, 256, mode=mode)
+    one = equilib_b200.equi2cube2equi(img[1], rots[1], 64, 128, 256, mode=mode, fused=True)
     cube = equilib_b200.equi2cube(img[1], rots[1], 64, "horizon", mode=mode, fast_coords=False)
     assert torch.equal(one, equilib_b200.cube2equi(cube, "horizon", 128, 256, mode=mode))
     # class API, z_down
     obj = equilib_b200.Equi2Cube2Equi(64, 128, 256, z_down=True, mode=mode)
     cube = equilib_b200.equi2cube(img, rots, 64, "horizon", z_down=True, mode=mode,
                                   fast_coords=False)
-    assert torch.equal(obj(img, rots), equilib_b200.cube2equi(cube, "horizon", 128, 256, mode=mode))
+    two = equilib_b200.cube2equi(cube, "horizon", 128, 256, mode=mode)
+    assert torch.equal(obj(img, rots, fused=True), two)
+    # fused=None: nearest fused, bilinear through the two launches (default coordinates)
+    auto = obj(img, rots)
+    if mode == "nearest" or dtype == "float32":
+        assert torch.equal(auto, two)
+    else:
+        d = (auto.float() - two.float()).abs()
+        assert float((d <= (1.0 if dtype == "uint8" else 2.0 ** -7)).float().mean()) >= 0.9995
 
 
 def test_fused_cube_chain_vs_oracle_composition():
@@ -1041,8 +1051,10 @@ def test_fused_cube_chain_vs_oracle_composition():
     rots = HARD_ROTS[1:3]
     cube = oracle.equi2cube(torch.from_numpy(img), rots, 128, "horizon", flavour="cuda")
     ref = oracle.cube2equi(cube, "horizon", 256, 512, flavour="cuda")
-    out = equilib_b200.equi2cube2equi(torch.from_numpy(img).to(DEV), rots, 128, 256, 512)
-    assert helpers.frac_close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-5) >= 0.999
+    for fused in (True, None):
+        out = equilib_b200.equi2cube2equi(torch.from_numpy(img).to(DEV), rots, 128, 256, 512,
+                                          fused=fused)
+        assert helpers.frac_close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=2e-5) >= 0.999
     # bicubic and exact_clip take the two launches behind the same entry point
     out = equilib_b200.equi2cube2equi(torch.from_numpy(img).to(DEV), rots, 128, 256, 512,
                                       mode="bicubic")

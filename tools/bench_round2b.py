@@ -107,7 +107,7 @@ def main():
                 cube = equilib_b200.equi2cube(x, r, 1024, "horizon", mode=mode, fast_coords=fast)
                 return equilib_b200.cube2equi(cube, "horizon", h, w, mode=mode)
             def one():
-                return equilib_b200.equi2cube2equi(x, r, 1024, h, w, mode=mode)
+                return equilib_b200.equi2cube2equi(x, r, 1024, h, w, mode=mode, fused=True)
             alg = 2 * x.numel() * es
             name = f"N2: equi->cube(1024)->equi {mode} {str(dtype)[6:]} {b}x3x{h}x{w}"
             report(name + " [two launches, default coordinates]", timed(two), b * h * w, alg)
