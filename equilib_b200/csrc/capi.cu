@@ -454,8 +454,9 @@ static bool can_lean2(const eqb_remap_desc* d) {
   if (d->flags & (EQB_FLAG_NO_STAGE | EQB_FLAG_NO_TMA | EQB_FLAG_NO_LEAN | EQB_FLAG_NO_LEAN2 |
                   EQB_FLAG_CHANNELS_LAST))
     return false;
-  if (d->transform > EQB_EQUI2CUBE) return false;
   const bool cubic = d->mode == EQB_BICUBIC;
+  // pers2equi: bicubic only (fill tiles cost no divide, no tap; the in-view ones read boxes)
+  if (d->transform > EQB_EQUI2CUBE && !(d->transform == EQB_PERS2EQUI && cubic)) return false;
   if (!cubic && (d->mode != EQB_BILINEAR || d->clip)) return false;
   if (d->channels != 1 && d->channels != 3 && d->channels != 4) return false;
   if (!encode_tiled()) return false;
@@ -518,7 +519,7 @@ template <int XF> static cudaError_t go(Params& p, const eqb_remap_desc* d, int 
   if (can_lean2(d)) {
     setup_tma_l2(d, p);
     if (p.use_tma) {
-      const bool exact = (d->flags & EQB_FLAG_EXACT_COORDS) ||
+      const bool exact = (d->flags & EQB_FLAG_EXACT_COORDS) || XF == EQB_PERS2EQUI ||
                          (d->dtype == EQB_F32 && !(d->flags & EQB_FLAG_FAST_COORDS));
       return launch_lean2<XF>(p, d->dtype, exact, d->mode, s);
     }

@@ -106,7 +106,8 @@ constexpr L2Weights make_l2_weights() {
 }
 static __device__ const L2Weights g_l2_weights = make_l2_weights();
 
-enum : int { L2_SMOOTH = 1, L2_BORDER = 2, L2_STRADDLE = 4, L2_RAGGED = 8, L2_BACKGROUND = 16 };
+enum : int { L2_SMOOTH = 1, L2_BORDER = 2, L2_STRADDLE = 4, L2_RAGGED = 8, L2_BACKGROUND = 16,
+              L2_FILL = 32 };
 
 // (barriers are addressed by their 32-bit shared-memory address, computed once per kernel:
 // re-deriving it from a generic pointer at every use was 3 % of the issued instructions)
@@ -197,6 +198,66 @@ __device__ __forceinline__ void node_coords2(const Params& p, const RowCtx<XF>& 
     }
     coords2<XF, false>(p, c, x0, x1, cell, rc[0], rc[1], ui, uj);
   }
+}
+
+// pers2equi (XF == EQB_PERS2EQUI, bicubic, exact chain): a NODE carries the projective
+// coordinates of its ray where it looks into the camera's half space -- they only feed the tile
+// headers (hull, smoothness, box), never a pixel, so the quotient need not be the IEEE one --
+// else a negative sentinel (such tiles take the general path), and a mask of the "outside the
+// field of view" conditions it satisfies with the room pers2equi_run_surely_outside() asks of
+// the two ends of an 8-pixel run: a tile whose nodes (every 8th column of every row) all share
+// one condition is fill (out[mask] = 0, then the clamp: pers2equi/torch.py:232-251) -- 92 % of
+// an 8K output at fov 90 -- and costs no divide, no tap and no per-pixel test.
+__device__ __forceinline__ void pers_node(const Params& p, const RowCtx<EQB_PERS2EQUI>& c, int x,
+                                          float& ui, float& uj, unsigned& mask) {
+  const int xw = x < 0 ? x + p.dw : (x >= p.dw ? x - p.dw : x);
+  const float2 cs = __ldg(reinterpret_cast<const float2*>(p.tx) + xw);
+  const float dth = (float)kL2Step * (kTwoPi / (float)p.dw);
+  const float room = 0.25f * dth * dth * fabsf(c.r0) *
+                         (fabsf(c.A[0]) + fabsf(c.A[1]) + fabsf(c.A[3]) + fabsf(c.A[4]) +
+                          (p.swf + p.shf) * (fabsf(c.A[6]) + fabsf(c.A[7]))) + 1e-3f;
+  const float mx = c.r0 * cs.x, my = c.r0 * cs.y;
+  const float X = c.A[0] * mx + c.A[1] * my + c.z0;
+  const float Y = c.A[3] * mx + c.A[4] * my + c.z1;
+  const float Z = c.A[6] * mx + c.A[7] * my + c.z2;
+  const float wl = p.swf - 0.499f, hl = p.shf - 0.499f;
+  mask = (Z < -room ? 1u : 0u) | (X + 0.501f * Z < -room ? 2u : 0u) |
+         (wl * Z - X < -room ? 4u : 0u) | (Y + 0.501f * Z < -room ? 8u : 0u) |
+         (hl * Z - Y < -room ? 16u : 0u);
+  ui = uj = -1.0e4f;
+  if (Z > 1e-6f) {
+    const float rz = __frcp_rn(Z);
+    ui = fminf(fmaxf(fmaf(X, rz, 0.5f), -1.0e4f), 1.0e5f);
+    uj = fminf(fmaxf(fmaf(Y, rz, 0.5f), -1.0e4f), 1.0e5f);
+  }
+}
+
+// The "outside" conditions of pers_node at one corner of a tile, with the room a 32 x 16 pixel
+// tile needs: each condition is a linear form L(M) < 0 and M = A . (cos phi cos theta, cos phi
+// sin theta, sin phi), so over the tile L stays below the bilinear interpolant of its four
+// corner values plus (dtheta^2 + dphi^2) / 8 times the sum of its coefficient magnitudes (the
+// second derivatives of a sinusoid; 1 / 4 here: a factor of two in hand).  Four corners sharing
+// one condition with that room make the whole tile fill.
+__device__ __forceinline__ unsigned pers_corner_mask(const Params& p, int b, int x, int y) {
+  float A[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = __ldg(p.mats + (long long)b * 9 + i);
+  const int xw = x >= p.dw ? x - p.dw : x;
+  const float2 cs = __ldg(reinterpret_cast<const float2*>(p.tx) + xw);
+  const float cphi = __ldg(p.ty + y), sphi = __ldg(p.ty + p.dh + y);
+  const float dth = (float)kL2TileW * (kTwoPi / (float)p.dw);
+  const float dph = (float)kL2TileH * (kPi / (float)p.dh);
+  const float amp = fabsf(A[0]) + fabsf(A[1]) + fabsf(A[2]) + fabsf(A[3]) + fabsf(A[4]) +
+                    fabsf(A[5]) + (p.swf + p.shf) * (fabsf(A[6]) + fabsf(A[7]) + fabsf(A[8]));
+  const float room = 0.25f * (dth * dth + dph * dph) * amp + 1e-3f;
+  const float mx = cphi * cs.x, my = cphi * cs.y;
+  const float X = A[0] * mx + A[1] * my + A[2] * sphi;
+  const float Y = A[3] * mx + A[4] * my + A[5] * sphi;
+  const float Z = A[6] * mx + A[7] * my + A[8] * sphi;
+  const float wl = p.swf - 0.499f, hl = p.shf - 0.499f;
+  return (Z < -room ? 1u : 0u) | (X + 0.501f * Z < -room ? 2u : 0u) |
+         (wl * Z - X < -room ? 4u : 0u) | (Y + 0.501f * Z < -room ? 8u : 0u) |
+         (hl * Z - Y < -room ? 16u : 0u);
 }
 
 // ---- taps --------------------------------------------------------------------------------
@@ -520,6 +581,7 @@ __device__ __noinline__ void l2_bicubic_general(const Params& p, float ix, float
 
 template <int XF, typename T, int NC, bool EXACT, int MODE>
 __global__ void __launch_bounds__(kL2Warps * 32,
+                                  XF == EQB_PERS2EQUI ? 4 :  // (two scalar chains with IEEE divides live)
                                   MODE == EQB_BICUBIC ? (l2_ctas(sizeof(T), true) < 5 ? l2_ctas(sizeof(T), true) : 5)
                                   : sizeof(T) == 4    ? (l2_ctas(4) < 5 ? l2_ctas(4) : 5)
                                                       : (EXACT ? 5 : 7))
@@ -534,6 +596,7 @@ __global__ void __launch_bounds__(kL2Warps * 32,
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // two box buffers
   __shared__ __align__(16) float2 nodes[kL2TileH][kL2Cols + 1];  // (ui, uj)
   __shared__ __align__(16) int4 headers[kL2MaxIters];
+  __shared__ unsigned char nmask[XF == EQB_PERS2EQUI ? kL2TileH : 1][kL2Cols + 1];  // pers_node
   __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -552,6 +615,41 @@ __global__ void __launch_bounds__(kL2Warps * 32,
     mbar_init(&empty_bar[1], kL2Warps);
   }
 
+  // ---- pers2equi: a strip whose tiles are all outside the field of view (most of them: the
+  // view covers 7.5 % of an 8K output at fov 90) needs no node, no header and no barrier but
+  // this one: the corners of its tiles decide
+  if constexpr (XF == EQB_PERS2EQUI && MODE == EQB_BICUBIC) {
+    bool fill_strip = strip_x0 + ntiles * kL2TileW <= p.dw && tile_y0 + kL2TileH <= p.dh;
+    if (fill_strip && tid < 32) {
+      // lane 2k + j: corner column k (0 .. ntiles), row j (top / bottom) of the strip
+      const int kc = lane >> 1, j = lane & 1;
+      unsigned m = 0x1fu;
+      if (kc <= ntiles)
+        m = pers_corner_mask(p, b, strip_x0 + kc * kL2TileW, min(tile_y0 + j * kL2TileH, p.dh - 1));
+      // tile k: corners 2k, 2k + 1, 2k + 2, 2k + 3
+      const unsigned m1 = __shfl_down_sync(0xffffffffu, m, 1);
+      const unsigned m2 = __shfl_down_sync(0xffffffffu, m, 2);
+      const unsigned m3 = __shfl_down_sync(0xffffffffu, m, 3);
+      const bool tile_fill = (m & m1 & m2 & m3) != 0u;
+      fill_strip = __all_sync(0xffffffffu, (lane & 1) || kc >= ntiles || tile_fill);
+    }
+    if (__syncthreads_and(fill_strip || tid >= 32)) {
+      const bool clip0 = p.clip != nullptr;
+      float lo0 = 0.f, hi0 = 0.f;
+      if (clip0) { lo0 = __ldg(p.clip); hi0 = __ldg(p.clip + 1); }
+      const int lx0 = lane & 15, ly0 = lane >> 4;
+      constexpr int P0 = sizeof(T) == 1 ? 2 : 1;
+      T* d = static_cast<T*>(p.dst) + (long long)b * p.dsb +
+             (long long)(tile_y0 + warp * 4 + ly0) * p.dsh + strip_x0 + lx0 * P0;
+      for (int k = 0; k < ntiles; ++k, d += kL2TileW)
+        for (int c = 0; c < NC; ++c) {
+          l2_store_pair<T>(d + c * p.dsc, 0.f, 0.f, clip0, lo0, hi0, p.flags);
+          l2_store_pair<T>(d + c * p.dsc + 2 * p.dsh, 0.f, 0.f, clip0, lo0, hi0, p.flags);
+        }
+      return;
+    }
+  }
+
   // ---- prologue 1: the exact chain at the strip's nodes -------------------------------
   if (!background) {
     const int row = tid & (kL2TileH - 1);
@@ -560,7 +658,15 @@ __global__ void __launch_bounds__(kL2Warps * 32,
     row_setup<XF>(p, b, y, rc);
     const int ncols = ntiles * 4 + 3;
     constexpr int STEP = kL2Warps * 32 / kL2TileH;  // columns a thread advances by
-    if constexpr (EXACT) {
+    if constexpr (XF == EQB_PERS2EQUI) {
+      for (int col = tid >> 4; col < ncols; col += STEP) {
+        float ui, uj;
+        unsigned mask;
+        pers_node(p, rc, strip_x0 + kL2Step * (col - 1), ui, uj, mask);
+        nodes[row][col] = make_float2(ui, uj);
+        nmask[row][col] = (unsigned char)mask;
+      }
+    } else if constexpr (EXACT) {
       // two nodes per packed chain (coords2)
       for (int col = tid >> 4; col < ncols; col += 2 * STEP) {
         const int col2 = col + STEP < ncols ? col + STEP : col;
@@ -600,6 +706,17 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       float2 n[5];
 #pragma unroll
       for (int i = 0; i < 5; ++i) n[i] = np[i];
+      if constexpr (XF == EQB_PERS2EQUI) {
+        // every node of the tile's own columns 0..4 outside the view by one common condition?
+        const unsigned char* mp = &nmask[r][k * 4 + c - 1];
+        const int o = c == 1 ? 1 : 0;
+        const unsigned common = __reduce_and_sync(
+            0xffffffffu, (unsigned)(mp[o] & mp[o + 1] & mp[o + 2] & mp[o + 3]));
+        if (common != 0u && !(flags & L2_RAGGED)) {
+          if (lane == 0) headers[k] = make_int4(0, 0, -1, flags | L2_FILL);
+          continue;
+        }
+      }
       float ulo = fminf(fminf(n[1].x, n[2].x), n[3].x), uhi = fmaxf(fmaxf(n[1].x, n[2].x), n[3].x);
       float vlo = fminf(fminf(n[1].y, n[2].y), n[3].y), vhi = fmaxf(fmaxf(n[1].y, n[2].y), n[3].y);
       const float2 e = c == 1 ? n[4] : n[0];  // the end node that is a column of the tile
@@ -730,6 +847,20 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       continue;
     }
 
+    if constexpr (XF == EQB_PERS2EQUI) {
+      if (flags & L2_FILL) {  // outside the field of view: out[mask] = 0, then the clamp
+        if constexpr (CUBIC) {
+          if (row0_ok)
+            for (int c = 0; c < NC; ++c) {
+              l2_store_pair<T>(d0 + c * p.dsc, 0.f, 0.f, clip, clip_lo, clip_hi, p.flags);
+              if (row1_ok)
+                l2_store_pair<T>(d1 + c * p.dsc, 0.f, 0.f, clip, clip_lo, clip_hi, p.flags);
+            }
+        }
+        continue;
+      }
+    }
+
     const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED | (CUBIC ? L2_BORDER : 0))) ==
                                             L2_SMOOTH
                                       : (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE |
@@ -761,6 +892,17 @@ __global__ void __launch_bounds__(kL2Warps * 32,
         for (int gy = 0; gy < 2; ++gy) {
           const RowCtx<XF>& rc = rows[gy];
           const int xa = tile_x0 + xloc(2 * gy), xb = tile_x0 + xloc(2 * gy + 1);
+          if constexpr (XF == EQB_PERS2EQUI) {
+            // (every pixel of a smooth interior tile lies inside the field of view)
+            float uj, ui;
+            coords<XF, false>(p, rc, b, xa, 0, 0, 0, uj, ui);
+            ixa[2 * gy] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[2 * gy] = to_index(uj, p.inv_hm1, p.shm1f);
+            coords<XF, false>(p, rc, b, xb, 0, 0, 0, uj, ui);
+            ixa[2 * gy + 1] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[2 * gy + 1] = to_index(uj, p.inv_hm1, p.shm1f);
+            continue;
+          }
           float rca = 0.f, rcb = 0.f;
           if (XF == EQB_EQUI2CUBE) {
             rca = __ldg(p.tx + (xa - cell * p.w_face));
@@ -856,6 +998,7 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       const T* const box = reinterpret_cast<const T*>(smem_raw + (nbox & 1u) * BUF);
       const bool interp = !EXACT && (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE)) == L2_SMOOTH;
       float ixa[4], iya[4];
+      bool inval[4] = {false, false, false, false};  // pers2equi: outside the field of view
       if (interp) {
         const unsigned long long mone = pk2(-1.0f, -1.0f);
 #pragma unroll
@@ -882,6 +1025,16 @@ __global__ void __launch_bounds__(kL2Warps * 32,
           row_setup<XF>(p, b, yq, rc);
           const int xa = min(tile_x0 + xloc(2 * gy), p.dw - 1);
           const int xb = min(tile_x0 + xloc(2 * gy + 1), p.dw - 1);
+          if constexpr (XF == EQB_PERS2EQUI) {
+            float uj, ui;
+            inval[2 * gy] = coords<XF, false>(p, rc, b, xa, 0, 0, 0, uj, ui);
+            ixa[2 * gy] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[2 * gy] = to_index(uj, p.inv_hm1, p.shm1f);
+            inval[2 * gy + 1] = coords<XF, false>(p, rc, b, xb, 0, 0, 0, uj, ui);
+            ixa[2 * gy + 1] = to_index(ui, p.inv_wm1, p.swm1f);
+            iya[2 * gy + 1] = to_index(uj, p.inv_hm1, p.shm1f);
+            continue;
+          }
           float rca = 0.f, rcb = 0.f;
           if (XF == EQB_EQUI2CUBE) {
             rca = __ldg(p.tx + (xa - cell * p.w_face));
@@ -900,6 +1053,12 @@ __global__ void __launch_bounds__(kL2Warps * 32,
         const float ix = ixa[j], iy = iya[j];
         T* d = ((j >> 1) ? d1 : d0) + (xloc(j) - lx * P);
         if constexpr (CUBIC) {
+          if (XF == EQB_PERS2EQUI && inval[j]) {
+            const float fill = clip ? fminf(fmaxf(0.0f, clip_lo), clip_hi) : 0.0f;
+            const T o = OutCvt<T>::cvt(fill, p.flags);
+            for (int c = 0; c < NC; ++c) Pack<T, 1>::st(d + c * p.dsc, &o);
+            continue;
+          }
           l2_bicubic_general<T, NC>(p, ix, iy, boxed, box, pitch, bh, gx0, gy0, src_b, d, clip,
                                     clip_lo, clip_hi);
           continue;
