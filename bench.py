@@ -381,8 +381,10 @@ KERNELS = {
     ("equi2equi", "bilinear", 4): "eqb::remap_lean2_kernel<EQUI2EQUI,float,3,EXACT=1> (TMA boxes, "
                                   "exact coordinates)",
     ("equi2pers", "bilinear", 2): "eqb::remap_lean2_kernel<EQUI2PERS,T,3,EXACT=0>",
-    ("equi2pers", "bicubic", 1): "eqb::remap_staged_kernel<EQUI2PERS,BICUBIC,uint8_t>",
-    ("pers2equi", "bicubic", 1): "eqb::remap_kernel<PERS2EQUI,BICUBIC,uint8_t> (direct gather)",
+    ("equi2pers", "bicubic", 1): "eqb::remap_lean2_kernel<EQUI2PERS,uint8_t,3,EXACT=0,BICUBIC> "
+                                 "(4x4 taps from TMA boxes, strip-node coordinates)",
+    ("pers2equi", "bicubic", 1): "eqb::remap_lean2_kernel<PERS2EQUI,uint8_t,3,EXACT=1,BICUBIC> "
+                                 "(fill strips from tile corners, in-view tiles from TMA boxes)",
 }
 
 

@@ -59,8 +59,7 @@ class Options:
 
 def pop_options(kwargs: dict) -> Options:
     opt = Options(
-        exact_clip=bool(kwargs.pop("exact_clip",
-                                   os.environ.get("EQUILIB_B200_EXACT_CLIP") == "1")),
+        exact_clip=bool(kwargs.pop("exact_clip", _env(b"EQUILIB_B200_EXACT_CLIP") == b"1")),
         saturate_uint8=bool(kwargs.pop("saturate_uint8", False)),
         clip_group=kwargs.pop("clip_group", None),
         fast_coords=kwargs.pop("fast_coords", None),
@@ -196,32 +195,52 @@ def reduce_clip(out2: torch.Tensor, group) -> torch.Tensor:
     return allreduce_minmax(out2, None if group is True else group)
 
 
+# Environment switches are read on every call (tests and experiments flip them at run time).
+# os.environ.get() costs ~1.4 us per key (str -> bytes encoding + wrappers) and there are ten
+# of them: a third of the host time of a small launch (BASELINE config 1).  On POSIX the
+# mapping behind os.environ is a plain dict of bytes that putenv / monkeypatch keep in sync.
+_ENV_DATA = getattr(os.environ, "_data", None)
+if not (isinstance(_ENV_DATA, dict) and all(isinstance(k, bytes) for k in list(_ENV_DATA)[:4])):
+    _ENV_DATA = None
+
+
+def _env(name: bytes):
+    """Value of an EQUILIB_B200_* switch as bytes, or None."""
+    if _ENV_DATA is not None:
+        return _ENV_DATA.get(name)
+    v = os.environ.get(name.decode())
+    return None if v is None else v.encode()
+
+
+_ENV_FLAGS = (
+    (b"EQUILIB_B200_NO_STAGE", _lib.FLAG_NO_STAGE),
+    (b"EQUILIB_B200_NO_TMA", _lib.FLAG_NO_TMA),
+    (b"EQUILIB_B200_FORCE_STAGE", _lib.FLAG_FORCE_STAGE),
+    (b"EQUILIB_B200_NO_LEAN", _lib.FLAG_NO_LEAN),
+    (b"EQUILIB_B200_NO_LEAN2", _lib.FLAG_NO_LEAN2),
+    (b"EQUILIB_B200_FORCE_LEAN2", _lib.FLAG_FORCE_LEAN2),
+)
+
+
 def flags_of(dtype: torch.dtype, opt: "Options") -> int:
     flags = _lib.FLAG_SATURATE_U8 if (opt.saturate_uint8 and dtype == torch.uint8) else 0
     fast = opt.fast_coords
-    if fast is None and os.environ.get("EQUILIB_B200_FAST_COORDS") in ("0", "1"):
-        fast = os.environ["EQUILIB_B200_FAST_COORDS"] == "1"
+    if fast is None:
+        e = _env(b"EQUILIB_B200_FAST_COORDS")
+        if e == b"0" or e == b"1":
+            fast = e == b"1"
     if fast is True:
         flags |= _lib.FLAG_FAST_COORDS
     elif fast is False:
         flags |= _lib.FLAG_EXACT_COORDS
     # experiments only: EQUILIB_B200_WARP_SHAPE = 1 (32x1), 2 (16x2), 3 (8x4) forces the
     # warp tile shape; unset/0 lets the library choose
-    ws = os.environ.get("EQUILIB_B200_WARP_SHAPE")
+    ws = _env(b"EQUILIB_B200_WARP_SHAPE")
     if ws:
         flags |= (int(ws) & 3) << _lib.FLAG_WARP_SHAPE_SHIFT
-    if os.environ.get("EQUILIB_B200_NO_STAGE") == "1":
-        flags |= _lib.FLAG_NO_STAGE
-    if os.environ.get("EQUILIB_B200_NO_TMA") == "1":
-        flags |= _lib.FLAG_NO_TMA
-    if os.environ.get("EQUILIB_B200_FORCE_STAGE") == "1":
-        flags |= _lib.FLAG_FORCE_STAGE
-    if os.environ.get("EQUILIB_B200_NO_LEAN") == "1":
-        flags |= _lib.FLAG_NO_LEAN
-    if os.environ.get("EQUILIB_B200_NO_LEAN2") == "1":
-        flags |= _lib.FLAG_NO_LEAN2
-    if os.environ.get("EQUILIB_B200_FORCE_LEAN2") == "1":
-        flags |= _lib.FLAG_FORCE_LEAN2
+    for name, bit in _ENV_FLAGS:
+        if _env(name) == b"1":
+            flags |= bit
     return flags
 
 

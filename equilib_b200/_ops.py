@@ -35,6 +35,20 @@ def dtype_code(dt: torch.dtype) -> int:
         ) from None
 
 
+def _raw_stream(index: int) -> int:
+    """cudaStream_t of torch's current stream on device ``index`` (what
+    ``torch.cuda.current_stream(dev).cuda_stream`` returns, without building a Stream object:
+    0.3 us instead of 7 us per launch)."""
+    return _get_raw_stream(index)
+
+
+try:
+    _get_raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # (a torch build without the private accessor)
+    def _get_raw_stream(index: int) -> int:
+        return torch.cuda.current_stream(torch.device("cuda", index)).cuda_stream
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -134,12 +148,12 @@ def _remap_impl(
     d.itab_x, d.grid, d.clip = _ptr(itab_x), _ptr(grid), _ptr(clip)
     d.face_ptrs = _ptr(face_ptrs)
     if torch.cuda.current_device() == dev.index:
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.lib().eqb_remap(C.byref(d), C.c_void_p(stream)), "eqb_remap")
+        status = _lib.lib().eqb_remap(C.byref(d), _raw_stream(dev.index))
     else:
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            _lib.check(_lib.lib().eqb_remap(C.byref(d), C.c_void_p(stream)), "eqb_remap")
+            status = _lib.lib().eqb_remap(C.byref(d), _raw_stream(dev.index))
+    if status != 0:
+        _lib.check(status, "eqb_remap")
 
 
 def supports_channels_last(src, out, mats, tab_x, tab_y, itab_x, grid, clip, face_ptrs,
