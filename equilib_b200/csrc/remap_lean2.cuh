@@ -938,7 +938,8 @@ __global__ void __launch_bounds__(kL2Warps * 32,
           else l2_px_setup<T>(a, px[j]);
         }
       }
-      // request the next box, then wait for this one
+      // request the next box, then wait for this one (requesting it before this tile's
+      // coordinates instead changes nothing: 1.384 vs 1.371 ms on the headline workload)
       if (tid == 0) {
         const int k2 = next_boxed(k);
         if (k2 >= 0) issue(k2, nbox + 1);

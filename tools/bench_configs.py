@@ -106,7 +106,14 @@ def main():
             ms = timed(lambda: equilib_b200.equi2equi(src, rr))
             report("2: equi2equi bfloat16 b32 4K bilinear, views rolled by a further 0.96 rad", ms,
                    b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 2)
+        if dtype != torch.float32:
+            ms = timed(lambda: equilib_b200.equi2equi(src, r, mode="bicubic", fast_coords=False))
+            report(f"2: equi2equi {str(dtype)[6:]} b{b} 4K bicubic fast_coords=False (exact chain)",
+                   ms, b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * src.element_size())
         if dtype == torch.float32:
+            ms = timed(lambda: equilib_b200.equi2equi(src, r, mode="bicubic", fast_coords=True))
+            report("2: equi2equi float32 b16 4K bicubic fast_coords=True (opt-in)", ms,
+                   b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 4)
             ms = timed(lambda: equilib_b200.equi2equi(src, r, fast_coords=True))
             report("2: equi2equi float32 b16 4K bilinear fast_coords=True (opt-in)", ms,
                    b * 2048 * 4096, 2 * b * 2048 * 4096 * 3 * 4)
@@ -200,6 +207,22 @@ def main():
                 report(f"3: cube2equi {str(dtype)[6:]} b16 w1024 {fmt} -> 4K {mode}", ms,
                        16 * 2048 * 4096, 16 * 3 * (2048 * 4096 + 6 * 1024 * 1024) * es)
             del cube
+        # the round trip as ONE call: nearest runs the fused kernel (no cubemap
+        # in memory), bilinear the two launches (equi2cube2equi picks by measurement)
+        for mode in ("nearest", "bilinear"):
+            alg = 2 * 16 * 3 * 2048 * 4096 * es
+            ms = timed(lambda: equilib_b200.equi2cube2equi(equi, r, 1024, 2048, 4096, mode=mode),
+                       steps=5)
+            report(f"3+N2: equi -> cube(1024) -> equi {str(dtype)[6:]} b16 4K {mode}, "
+                   "equi2cube2equi (default)", ms, 16 * 2048 * 4096, alg)
+            ms = timed(lambda: equilib_b200.equi2cube2equi(equi, r, 1024, 2048, 4096, mode=mode,
+                                                           fused=True), steps=5)
+            report(f"3+N2: equi -> cube(1024) -> equi {str(dtype)[6:]} b16 4K {mode}, fused=True "
+                   "(one launch, no cubemap)", ms, 16 * 2048 * 4096, alg)
+            ms = timed(lambda: equilib_b200.equi2cube2equi(equi, r, 1024, 2048, 4096, mode=mode,
+                                                           fused=False), steps=5)
+            report(f"3+N2: equi -> cube(1024) -> equi {str(dtype)[6:]} b16 4K {mode}, fused=False "
+                   "(two launches)", ms, 16 * 2048 * 4096, alg)
         del equi
 
     # config 4 (per GPU share: 8 frames of 3x4096x8192 uint8, bicubic)
