@@ -232,34 +232,6 @@ __device__ __forceinline__ void pers_node(const Params& p, const RowCtx<EQB_PERS
   }
 }
 
-// The "outside" conditions of pers_node at one corner of a tile, with the room a 32 x 16 pixel
-// tile needs: each condition is a linear form L(M) < 0 and M = A . (cos phi cos theta, cos phi
-// sin theta, sin phi), so over the tile L stays below the bilinear interpolant of its four
-// corner values plus (dtheta^2 + dphi^2) / 8 times the sum of its coefficient magnitudes (the
-// second derivatives of a sinusoid; 1 / 4 here: a factor of two in hand).  Four corners sharing
-// one condition with that room make the whole tile fill.
-__device__ __forceinline__ unsigned pers_corner_mask(const Params& p, int b, int x, int y) {
-  float A[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) A[i] = __ldg(p.mats + (long long)b * 9 + i);
-  const int xw = x >= p.dw ? x - p.dw : x;
-  const float2 cs = __ldg(reinterpret_cast<const float2*>(p.tx) + xw);
-  const float cphi = __ldg(p.ty + y), sphi = __ldg(p.ty + p.dh + y);
-  const float dth = (float)kL2TileW * (kTwoPi / (float)p.dw);
-  const float dph = (float)kL2TileH * (kPi / (float)p.dh);
-  const float amp = fabsf(A[0]) + fabsf(A[1]) + fabsf(A[2]) + fabsf(A[3]) + fabsf(A[4]) +
-                    fabsf(A[5]) + (p.swf + p.shf) * (fabsf(A[6]) + fabsf(A[7]) + fabsf(A[8]));
-  const float room = 0.25f * (dth * dth + dph * dph) * amp + 1e-3f;
-  const float mx = cphi * cs.x, my = cphi * cs.y;
-  const float X = A[0] * mx + A[1] * my + A[2] * sphi;
-  const float Y = A[3] * mx + A[4] * my + A[5] * sphi;
-  const float Z = A[6] * mx + A[7] * my + A[8] * sphi;
-  const float wl = p.swf - 0.499f, hl = p.shf - 0.499f;
-  return (Z < -room ? 1u : 0u) | (X + 0.501f * Z < -room ? 2u : 0u) |
-         (wl * Z - X < -room ? 4u : 0u) | (Y + 0.501f * Z < -room ? 8u : 0u) |
-         (hl * Z - Y < -room ? 16u : 0u);
-}
-
 // ---- taps --------------------------------------------------------------------------------
 // Sampling state of one pixel on the fast path: the word addresses of its left and right taps
 // (row y0, channel 0) and the PRMT selectors that move the tap out of its word.
@@ -625,7 +597,8 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       const int kc = lane >> 1, j = lane & 1;
       unsigned m = 0x1fu;
       if (kc <= ntiles)
-        m = pers_corner_mask(p, b, strip_x0 + kc * kL2TileW, min(tile_y0 + j * kL2TileH, p.dh - 1));
+        m = pers_corner_mask(p, b, strip_x0 + kc * kL2TileW,
+                              min(tile_y0 + j * kL2TileH, p.dh - 1), kL2TileW, kL2TileH);
       // tile k: corners 2k, 2k + 1, 2k + 2, 2k + 3
       const unsigned m1 = __shfl_down_sync(0xffffffffu, m, 1);
       const unsigned m2 = __shfl_down_sync(0xffffffffu, m, 2);

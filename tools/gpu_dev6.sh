@@ -30,4 +30,8 @@ for dt in (torch.uint8, torch.float32, torch.bfloat16):
             else: os.environ.pop("EQUILIB_B200_NO_LEAN2", None)
             ms = timed(lambda: equilib_b200.pers2equi(pers, r, 4096, 8192, fov, mode="bicubic"))
             print(f"pers2equi bicubic {dt} fov {fov} no_lean2={no or 0}: {ms:.3f} ms", flush=True)
+        os.environ.pop("EQUILIB_B200_NO_LEAN2", None)
+        for mode in ("nearest", "bilinear"):
+            ms = timed(lambda: equilib_b200.pers2equi(pers, r, 4096, 8192, fov, mode=mode))
+            print(f"pers2equi {mode} {dt} fov {fov}: {ms:.3f} ms", flush=True)
 PY
