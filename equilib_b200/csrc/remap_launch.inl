@@ -2,7 +2,7 @@
 // transform and its mode/dtype/PX/warp-shape dispatch (one translation unit per
 // transform so the six compile in parallel).
 #include "remap_kernels.cuh"
-#if EQB_XF <= 2 || EQB_XF == 4
+#if EQB_XF <= 4
 #include "remap_lean2.cuh"
 #endif
 
@@ -181,7 +181,7 @@ cudaError_t launch_nhwc<EQB_XF>(const Params& p, cudaStream_t stream) {
 }
 
 // ---- remap_lean2_kernel (remap_lean2.cuh) ---------------------------------------------------
-#if EQB_XF <= 2 || EQB_XF == 4
+#if EQB_XF <= 4
 template <int XF, typename T, int NC, bool EXACT, int MODE>
 static cudaError_t launch_lean2_one(Params p, cudaStream_t stream) {
   const long long tiles_x = (p.dw + kL2TileW - 1) / kL2TileW;
@@ -215,6 +215,14 @@ static cudaError_t launch_lean2_t(const Params& p, bool exact, cudaStream_t stre
       case 4: return launch_lean2_one<XF, T, 4, true, EQB_BICUBIC>(p, stream);
     }
     return cudaErrorNotSupported;
+  } else if constexpr (XF == EQB_CUBE2EQUI) {  // the tables ARE the exact coordinates
+    if (!exact) return cudaErrorNotSupported;
+    switch (p.C) {
+      case 1: return launch_lean2_one<XF, T, 1, true, MODE>(p, stream);
+      case 3: return launch_lean2_one<XF, T, 3, true, MODE>(p, stream);
+      case 4: return launch_lean2_one<XF, T, 4, true, MODE>(p, stream);
+    }
+    return cudaErrorNotSupported;
   } else {
     switch (p.C * 2 + (exact ? 1 : 0)) {
       case 2: return launch_lean2_one<XF, T, 1, false, MODE>(p, stream);
@@ -246,7 +254,7 @@ cudaError_t launch_lean2<EQB_XF>(const Params& p, int dtype, bool exact, int mod
 #if EQB_XF <= 2
   if (mode == EQB_BICUBIC) return launch_lean2_m<EQB_XF, EQB_BICUBIC>(p, dtype, exact, stream);
   if (mode == EQB_BILINEAR) return launch_lean2_m<EQB_XF, EQB_BILINEAR>(p, dtype, exact, stream);
-#elif EQB_XF == 4
+#elif EQB_XF == 3 || EQB_XF == 4
   if (mode == EQB_BICUBIC) return launch_lean2_m<EQB_XF, EQB_BICUBIC>(p, dtype, exact, stream);
 #endif
   return cudaErrorNotSupported;

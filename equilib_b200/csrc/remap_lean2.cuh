@@ -639,6 +639,15 @@ __global__ void __launch_bounds__(kL2Warps * 32,
         nodes[row][col] = make_float2(ui, uj);
         nmask[row][col] = (unsigned char)mask;
       }
+    } else if constexpr (XF == EQB_CUBE2EQUI) {
+      // coordinates from the 1-D tables (no transcendental); columns continue periodically
+      for (int col = tid >> 4; col < ncols; col += STEP) {
+        const int x = strip_x0 + kL2Step * (col - 1);
+        const int xw = x < 0 ? x + p.dw : (x >= p.dw ? x - p.dw : x);
+        float uj, ui;
+        coords<XF, false>(p, rc, b, xw, y, 0, 0, uj, ui);
+        nodes[row][col] = make_float2(ui, uj);
+      }
     } else if constexpr (EXACT) {
       // two nodes per packed chain (coords2)
       for (int col = tid >> 4; col < ncols; col += 2 * STEP) {
@@ -865,13 +874,15 @@ __global__ void __launch_bounds__(kL2Warps * 32,
         for (int gy = 0; gy < 2; ++gy) {
           const RowCtx<XF>& rc = rows[gy];
           const int xa = tile_x0 + xloc(2 * gy), xb = tile_x0 + xloc(2 * gy + 1);
-          if constexpr (XF == EQB_PERS2EQUI) {
-            // (every pixel of a smooth interior tile lies inside the field of view)
+          if constexpr (XF == EQB_PERS2EQUI || XF == EQB_CUBE2EQUI) {
+            // scalar chains (pers2equi: every pixel of a smooth interior tile lies inside the
+            // field of view)
+            const int y = min(y0q + 2 * gy, p.dh - 1);
             float uj, ui;
-            coords<XF, false>(p, rc, b, xa, 0, 0, 0, uj, ui);
+            coords<XF, false>(p, rc, b, xa, y, 0, 0, uj, ui);
             ixa[2 * gy] = to_index(ui, p.inv_wm1, p.swm1f);
             iya[2 * gy] = to_index(uj, p.inv_hm1, p.shm1f);
-            coords<XF, false>(p, rc, b, xb, 0, 0, 0, uj, ui);
+            coords<XF, false>(p, rc, b, xb, y, 0, 0, uj, ui);
             ixa[2 * gy + 1] = to_index(ui, p.inv_wm1, p.swm1f);
             iya[2 * gy + 1] = to_index(uj, p.inv_hm1, p.shm1f);
             continue;
@@ -999,12 +1010,12 @@ __global__ void __launch_bounds__(kL2Warps * 32,
           row_setup<XF>(p, b, yq, rc);
           const int xa = min(tile_x0 + xloc(2 * gy), p.dw - 1);
           const int xb = min(tile_x0 + xloc(2 * gy + 1), p.dw - 1);
-          if constexpr (XF == EQB_PERS2EQUI) {
+          if constexpr (XF == EQB_PERS2EQUI || XF == EQB_CUBE2EQUI) {
             float uj, ui;
-            inval[2 * gy] = coords<XF, false>(p, rc, b, xa, 0, 0, 0, uj, ui);
+            inval[2 * gy] = coords<XF, false>(p, rc, b, xa, yq, 0, 0, uj, ui);
             ixa[2 * gy] = to_index(ui, p.inv_wm1, p.swm1f);
             iya[2 * gy] = to_index(uj, p.inv_hm1, p.shm1f);
-            inval[2 * gy + 1] = coords<XF, false>(p, rc, b, xb, 0, 0, 0, uj, ui);
+            inval[2 * gy + 1] = coords<XF, false>(p, rc, b, xb, yq, 0, 0, uj, ui);
             ixa[2 * gy + 1] = to_index(ui, p.inv_wm1, p.swm1f);
             iya[2 * gy + 1] = to_index(uj, p.inv_hm1, p.shm1f);
             continue;
