@@ -13,6 +13,7 @@ done
 python bench.py --exact-coords --steps 20 --warmup 3 --no-cpu-baseline --no-e2e >> $O/bench_workloads.jsonl 2>> $O/bench_default.err
 python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
 python tools/rotation_sweep.py > $O/rotation_sweep.jsonl 2> $O/rotation_sweep.err
+python tools/bench_round2b.py > $O/round2b.jsonl 2> $O/round2b.err
 python tools/validate_vs_reference_cuda.py --ref baseline/_ref > $O/validate.jsonl 2> $O/validate.err
 # launch list of the bench command (share of the step per kernel), then full captures
 tail -3 $O/pytest_gpu.log

@@ -52,9 +52,12 @@ def main():
     for name, rots in fam.items():
         ms = timed(lambda: equilib_b200.equi2equi(src, rots))
         ms_exact = timed(lambda: equilib_b200.equi2equi(src, rots, fast_coords=False), steps=5)
+        ms_cubic = timed(lambda: equilib_b200.equi2equi(src, rots, mode="bicubic",
+                                                        clip_output=False), steps=5)
         print(json.dumps({"rotations": name, "ms": round(ms, 3),
                           "gpix_s": round(b * 2048 * 4096 / ms / 1e6, 1),
-                          "ms_exact_coords": round(ms_exact, 3)}), flush=True)
+                          "ms_exact_coords": round(ms_exact, 3),
+                          "ms_bicubic_no_clamp": round(ms_cubic, 3)}), flush=True)
 
 
 if __name__ == "__main__":
