@@ -1,0 +1,6 @@
+#!/bin/bash
+# ncu --set full capture of the pers2equi strip-node kernel (config 4)
+mkdir -p gpurun_out/ev
+O=gpurun_out/ev
+python bench.py --workload p2e_8k_u8_bicubic_b8 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/p2e_plain.json 2>&1 && ncu --set full --import-source on --clock-control none -k regex:remap_lean2 -s 3 -c 1 -o $O/prof_p2e -f python bench.py --workload p2e_8k_u8_bicubic_b8 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_p2e.log 2>&1
+ls -la $O
