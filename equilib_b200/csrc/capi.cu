@@ -455,6 +455,7 @@ static bool can_lean2(const eqb_remap_desc* d) {
                   EQB_FLAG_CHANNELS_LAST))
     return false;
   const bool cubic = d->mode == EQB_BICUBIC;
+  const bool nearest = d->mode == EQB_NEAREST && d->transform <= EQB_EQUI2CUBE;
   // pers2equi: bicubic only (fill tiles cost no divide, no tap; the in-view ones read boxes);
   // cube2equi: bicubic from a true horizon strip, which is one plain image (measured on 16 x 4K
   // from w_face 1024: bicubic fp32 2.74 -> 2.42 ms, bf16 2.56 -> 1.90, uint8 2.65 -> 2.06;
@@ -465,7 +466,9 @@ static bool can_lean2(const eqb_remap_desc* d) {
   } else if (d->transform > EQB_EQUI2CUBE && !(d->transform == EQB_PERS2EQUI && cubic)) {
     return false;
   }
-  if (!cubic && (d->mode != EQB_BILINEAR || d->clip)) return false;
+  // (nearest: a clamp cannot change a copied element; the host launches none)
+  if (!cubic && !nearest && (d->mode != EQB_BILINEAR || d->clip)) return false;
+  if (nearest && d->clip) return false;
   if (d->channels != 1 && d->channels != 3 && d->channels != 4) return false;
   if (!encode_tiled()) return false;
   const long long elt = (long long)elt_size(d->dtype), per16 = 16 / elt;
@@ -476,7 +479,7 @@ static bool can_lean2(const eqb_remap_desc* d) {
     // measured (gpurun_out/check_lean2.log): 2-byte stores of pixel pairs make the strip-node
     // kernel slower than the round-1 lean kernel on uint8 BILINEAR (1.71 vs 1.40 ms on the bench
     // rotations); it stays there unless asked for (EQB_FLAG_FORCE_LEAN2, experiments)
-    if (!cubic && !(d->flags & EQB_FLAG_FORCE_LEAN2)) return false;
+    if (!cubic && !nearest && !(d->flags & EQB_FLAG_FORCE_LEAN2)) return false;
     if (reinterpret_cast<uintptr_t>(d->dst) % 2) return false;
     if (d->dst_stride_b % 2 || d->dst_stride_c % 2 || d->dst_stride_h % 2) return false;
   }

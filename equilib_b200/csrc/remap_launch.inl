@@ -254,6 +254,7 @@ cudaError_t launch_lean2<EQB_XF>(const Params& p, int dtype, bool exact, int mod
 #if EQB_XF <= 2
   if (mode == EQB_BICUBIC) return launch_lean2_m<EQB_XF, EQB_BICUBIC>(p, dtype, exact, stream);
   if (mode == EQB_BILINEAR) return launch_lean2_m<EQB_XF, EQB_BILINEAR>(p, dtype, exact, stream);
+  if (mode == EQB_NEAREST) return launch_lean2_m<EQB_XF, EQB_NEAREST>(p, dtype, exact, stream);
 #elif EQB_XF == 3 || EQB_XF == 4
   if (mode == EQB_BICUBIC) return launch_lean2_m<EQB_XF, EQB_BICUBIC>(p, dtype, exact, stream);
 #endif

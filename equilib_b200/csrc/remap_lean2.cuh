@@ -50,6 +50,7 @@ constexpr int kL2Step = 8;                          // node spacing along x
 constexpr int kL2MaxIters = 8;                      // tiles per strip
 constexpr int kL2Cols = kL2MaxIters * 4 + 3;        // node columns -1 .. 4 * iters + 1
 constexpr int kL2Boxes = 11;
+constexpr int kL2TieCap = 256;                      // deferred pixels per strip (nearest)
 constexpr int kL2MinBoxH = kL2TileH + 5;            // an upright tile: 16 rows + 1 + margins
 static_assert(kL2Boxes <= kTmaSlots, "tensor-map slots");
 
@@ -107,7 +108,7 @@ constexpr L2Weights make_l2_weights() {
 static __device__ const L2Weights g_l2_weights = make_l2_weights();
 
 enum : int { L2_SMOOTH = 1, L2_BORDER = 2, L2_STRADDLE = 4, L2_RAGGED = 8, L2_BACKGROUND = 16,
-              L2_FILL = 32 };
+              L2_FILL = 32, L2_TIES = 64 };
 
 // (barriers are addressed by their 32-bit shared-memory address, computed once per kernel:
 // re-deriving it from a generic pointer at every use was 3 % of the issued instructions)
@@ -495,6 +496,53 @@ __device__ __forceinline__ void l2_bicubic_pair(unsigned ax, unsigned ay, float 
   }
 }
 
+// ---- nearest (MODE == EQB_NEAREST) ----------------------------------------------------------
+// Distance from a rounding tie below which an INTERPOLATED coordinate does not decide the tap
+// (the pixel gets the exact chain): 4e-3 px up to 4096-pixel sources -- the cubic's error on a
+// smooth tile is < 1e-3 px (header test) and the measured worst case against the exact chain,
+// rounding noise of both included, 1.7e-3 px at 4K -- growing with the source size like the
+// fp32 resolution of a coordinate (4.9e-4 px at 4K, 9.8e-4 px at 8K).
+__device__ __forceinline__ float l2_tie_guard(const Params& p) {
+  return 4e-3f * fmaxf(1.0f, fmaxf(p.swf, p.shf) * (1.0f / 4096.0f));
+}
+
+// The tap is the source pixel at (rint(iy), rint(ix)) -- nearbyint, like ATen -- and the output
+// element is that element, bit for bit: no conversion in either direction.  `a` = its byte
+// address in the box (channel 0), `plane` the bytes of one channel of the box.
+template <typename T> __device__ __forceinline__ T l2_lds_elem(unsigned a) {
+  if constexpr (sizeof(T) == 4) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return *reinterpret_cast<const T*>(&v);
+  } else if constexpr (sizeof(T) == 2) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return *reinterpret_cast<const T*>(&v);
+  } else {
+    unsigned short v;  // (no 8-bit register class: zero-extended into 16 bits)
+    asm volatile("ld.shared.u8 %0, [%1];" : "=h"(v) : "r"(a));
+    return (T)v;
+  }
+}
+
+// The lane's two pixels of one row from byte addresses ax, ay: 2- and 4-byte types d[0] and
+// d[16], uint8 the adjacent pair d[0..1].
+template <typename T, int NC>
+__device__ __forceinline__ void l2_nearest_pair(unsigned ax, unsigned ay, unsigned plane, T* d,
+                                                long long dsc) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const T t0 = l2_lds_elem<T>(ax + c * plane), t1 = l2_lds_elem<T>(ay + c * plane);
+    if constexpr (sizeof(T) == 1) {
+      const T t[2] = {t0, t1};
+      Pack<T, 2>::st(d + c * dsc, t);
+    } else {
+      Pack<T, 1>::st(d + c * dsc, &t0);
+      Pack<T, 1>::st(d + c * dsc + 16, &t1);
+    }
+  }
+}
+
 // One pixel on the general path (tiles at the source border, poles, seam; footprints that fit
 // no box): the 4 x 4 taps from the box where all of them lie inside it and none is reflected,
 // else from global memory, each tap reflected about 0 and size-1 like ATen.  One copy of the
@@ -560,6 +608,8 @@ __global__ void __launch_bounds__(kL2Warps * 32,
     remap_lean2_kernel(const __grid_constant__ Params p) {
   constexpr int ELT = (int)sizeof(T);
   constexpr bool CUBIC = MODE == EQB_BICUBIC;
+  constexpr bool NEAR = MODE == EQB_NEAREST;  // (hull and boxes as for bilinear: the tap is
+                                              // one of the two pixels around the coordinate)
   // taps of a pixel span [x - LO, x + HI] x [y - LO, y + HI] around its floored coordinate
   constexpr int LO = CUBIC ? 1 : 0, HI = CUBIC ? 2 : 1;
   constexpr int PER16 = 16 / ELT;
@@ -569,6 +619,9 @@ __global__ void __launch_bounds__(kL2Warps * 32,
   __shared__ __align__(16) float2 nodes[kL2TileH][kL2Cols + 1];  // (ui, uj)
   __shared__ __align__(16) int4 headers[kL2MaxIters];
   __shared__ unsigned char nmask[XF == EQB_PERS2EQUI ? kL2TileH : 1][kL2Cols + 1];  // pers_node
+  // nearest from interpolated coordinates: pixels deferred to the exact chain (see the fast path)
+  __shared__ unsigned short tie_list[MODE == EQB_NEAREST && !EXACT ? kL2TieCap : 1];
+  __shared__ int tie_count;
   __shared__ __align__(8) unsigned long long full_bar[2], empty_bar[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -585,6 +638,7 @@ __global__ void __launch_bounds__(kL2Warps * 32,
     mbar_init(&full_bar[1], 1);
     mbar_init(&empty_bar[0], kL2Warps);
     mbar_init(&empty_bar[1], kL2Warps);
+    tie_count = 0;
   }
 
   // ---- pers2equi: a strip whose tiles are all outside the field of view (most of them: the
@@ -731,6 +785,18 @@ __global__ void __launch_bounds__(kL2Warps * 32,
         ok = ok && fmaxf(fabsf(d4x), fabsf(d4y)) < 0.03f && fmaxf(fabsf(d2x), fabsf(d2y)) < 1.5f;
       }
       if (__all_sync(0xffffffffu, ok)) flags |= L2_SMOOTH;
+      if constexpr (MODE == EQB_NEAREST && !EXACT) {
+        // every node of the tile within the tie guard of a rounding tie (in x or in y): so is
+        // (nearly) every pixel -- the tile takes the exact chain (see the fast path)
+        bool nt = true;
+        const float guard = l2_tie_guard(p);
+#pragma unroll
+        for (int i = 1; i <= 3; ++i) {
+          const float tx = n[i].x - floorf(n[i].x), ty = n[i].y - floorf(n[i].y);
+          nt = nt && (fabsf(tx - 0.5f) < guard || fabsf(ty - 0.5f) < guard);
+        }
+        if (__all_sync(0xffffffffu, nt)) flags |= L2_TIES;
+      }
       if (straddle) flags |= L2_STRADDLE;
       // (bicubic: a tap within LO / HI pixels of the source border would be reflected)
       constexpr float BM = CUBIC ? 2.0f : 1.0f;
@@ -846,7 +912,7 @@ __global__ void __launch_bounds__(kL2Warps * 32,
     const bool fast = boxed && (EXACT ? (flags & (L2_SMOOTH | L2_RAGGED | (CUBIC ? L2_BORDER : 0))) ==
                                             L2_SMOOTH
                                       : (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE |
-                                                  L2_RAGGED)) == L2_SMOOTH);
+                                                  L2_RAGGED | L2_TIES)) == L2_SMOOTH);
     if (fast) {
       // ======== fast path: smooth tile with a box ==========================================
       float ixa[4], iya[4];
@@ -898,6 +964,69 @@ __global__ void __launch_bounds__(kL2Warps * 32,
           iya[2 * gy] = j2[0]; iya[2 * gy + 1] = j2[1];
         }
       }
+      if constexpr (NEAR && !EXACT) {
+        // ---- nearest from interpolated coordinates: the tap is a rounding decision, so every
+        // pixel whose interpolated coordinate lies within l2_tie_guard() of a rounding tie --
+        // more than twice the measured worst-case distance between the interpolated and the
+        // exact coordinate (1.7e-3 px at 4K, test_fast_coordinates_error_in_pixels) -- gets the exact
+        // chain; all others round like it (test_nearest_4k_tie_guard_equals_the_exact_chain).
+        // Such pixels are 1.6 % of a typical view.  A warp that ran the chain for them at once
+        // would still pay all of its ~150 instructions for one or two busy lanes (measured:
+        // 1.50 ms against 1.64 for the exact kernel), so they are DEFERRED: their positions
+        // go to a per-strip list in shared memory, the tile stores their provisional values
+        // like everybody else's, and after the last tile all 128 threads evaluate the exact
+        // chain for one listed pixel each and overwrite it.  Tiles whose NODES all sit on a
+        // tie (identity, pure yaw: every row coordinate is y + 0.5) are flagged L2_TIES by the
+        // prologue and never come here (general path, exact chain); a tile with more than 32
+        // such pixels per warp, or a full list, takes the packed exact chain below.
+        const float kTieGuard = l2_tie_guard(p);
+        bool tie[4];
+        unsigned mk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float tx = ixa[j] - floorf(ixa[j]), ty = iya[j] - floorf(iya[j]);
+          tie[j] = fabsf(tx - 0.5f) < kTieGuard || fabsf(ty - 0.5f) < kTieGuard;
+          mk[j] = __ballot_sync(0xffffffffu, tie[j]);
+        }
+        if (mk[0] | mk[1] | mk[2] | mk[3]) {  // (warp-uniform)
+          const int c0 = __popc(mk[0]), c1 = c0 + __popc(mk[1]), c2 = c1 + __popc(mk[2]);
+          const int total = c2 + __popc(mk[3]);
+          int base = kL2TieCap;
+          if (total <= 32) {
+            if (lane == 0) base = atomicAdd(&tie_count, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+          }
+          if (base + total <= kL2TieCap) {
+            // deferred: (tile, row, column) of each such pixel
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (tie[j]) {
+                const int off = j == 0 ? 0 : (j == 1 ? c0 : (j == 2 ? c1 : c2));
+                const int idx = base + off + __popc(mk[j] & ((1u << lane) - 1u));
+                tie_list[idx] = (unsigned short)((k << 9) | ((row0 + 2 * (j >> 1)) << 5) | xloc(j));
+              }
+          } else {
+            // the list is full, or most of the tile sits on a tie: exact chain for the tile
+            if (total <= 32 && base < kL2TieCap)  // (slots reserved above stay unused)
+              for (int i = base + lane; i < kL2TieCap; i += 32) tie_list[i] = 0xffffu;
+#pragma unroll 1
+            for (int gy = 0; gy < 2; ++gy) {
+              RowCtx<XF> rcx;
+              row_setup<XF>(p, b, min(y0q + 2 * gy, p.dh - 1), rcx);
+              const int xa = tile_x0 + xloc(2 * gy), xb = tile_x0 + xloc(2 * gy + 1);
+              float rca = 0.f, rcb = 0.f;
+              if (XF == EQB_EQUI2CUBE) {
+                rca = __ldg(p.tx + (xa - cell * p.w_face));
+                rcb = __ldg(p.tx + (xb - cell * p.w_face));
+              }
+              float i2[2], j2[2];
+              coords2<XF, true>(p, rcx, xa, xb, cell, rca, rcb, i2, j2);
+              ixa[2 * gy] = i2[0]; ixa[2 * gy + 1] = i2[1];
+              iya[2 * gy] = j2[0]; iya[2 * gy + 1] = j2[1];
+            }
+          }
+        }
+      }
       L2Px px[4];
       unsigned pa[4];  // bicubic: byte address of the top-left tap (x - 1, y - 1), channel 0
       float fx[4], fy[4];
@@ -910,6 +1039,11 @@ __global__ void __launch_bounds__(kL2Warps * 32,
             (int)(tile_s + (nbox & 1u) * BUF) - ((gy0 + LO) * pitch + gx0 + LO) * ELT;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          if constexpr (NEAR) {  // nearbyint, like ATen (taps_setup)
+            const int xi = __float2int_rn(ixa[j]), yi = __float2int_rn(iya[j]);
+            pa[j] = (unsigned)((yi * pitch + xi) * ELT + base);
+            continue;
+          }
           float xf = floorf(ixa[j]), yf = floorf(iya[j]);
           if (EXACT && !CUBIC) {  // footprint shifted to x0 = W-2 at ix == W-1 (taps_setup)
             xf = fminf(xf, p.swm1f - 1.0f);
@@ -930,7 +1064,13 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       }
       __syncwarp();
       mbar_wait_backoff(full_s + (nbox & 1u) * 8u, (nbox >> 1) & 1u);
-      if constexpr (CUBIC) {
+      if constexpr (NEAR) {
+        if (row0_ok) {
+          const unsigned plane = (unsigned)(p.tma_bw[m] * p.tma_bh[m] * ELT);
+          l2_nearest_pair<T, NC>(pa[0], pa[1], plane, d0, p.dsc);
+          if (row1_ok) l2_nearest_pair<T, NC>(pa[2], pa[3], plane, d1, p.dsc);
+        }
+      } else if constexpr (CUBIC) {
         if (row0_ok) {
           const unsigned row = (unsigned)(p.tma_bw[m] * ELT);
           const unsigned plane = row * (unsigned)p.tma_bh[m];
@@ -981,7 +1121,9 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       const int pitch = boxed ? p.tma_bw[m] : 0;
       const int bh = boxed ? p.tma_bh[m] : 0;
       const T* const box = reinterpret_cast<const T*>(smem_raw + (nbox & 1u) * BUF);
-      const bool interp = !EXACT && (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE)) == L2_SMOOTH;
+      // (nearest: the exact chain here -- the tie guard lives on the fast path only)
+      const bool interp =
+          !EXACT && !NEAR && (flags & (L2_SMOOTH | L2_BORDER | L2_STRADDLE)) == L2_SMOOTH;
       float ixa[4], iya[4];
       bool inval[4] = {false, false, false, false};  // pers2equi: outside the field of view
       if (interp) {
@@ -1048,6 +1190,18 @@ __global__ void __launch_bounds__(kL2Warps * 32,
                                     clip_lo, clip_hi);
           continue;
         }
+        if constexpr (NEAR) {
+          const int xi = __float2int_rn(ix), yi = __float2int_rn(iy);
+          const int xr = xi - gx0, yr = yi - gy0;
+          const bool from_box = boxed && xr >= 0 && xr < pitch && yr >= 0 && yr < bh;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const T o = from_box ? box[(c * bh + yr) * pitch + xr]
+                                 : __ldg(src_b + (long long)c * p.ssc + (yi * ssh + xi));
+            Pack<T, 1>::st(d + c * p.dsc, &o);
+          }
+          continue;
+        }
         const float xf = fminf(floorf(ix), p.swm1f - 1.0f), yf = fminf(floorf(iy), p.shm1f - 1.0f);
         const float bx = __fsub_rn(ix, xf), by = __fsub_rn(iy, yf);
         const float ax = __fsub_rn(1.0f, bx), ay = __fsub_rn(1.0f, by);
@@ -1089,6 +1243,34 @@ __global__ void __launch_bounds__(kL2Warps * 32,
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_s + (nbox & 1u) * 8u);
       ++nbox;
+    }
+  }
+
+  // ---- nearest from interpolated coordinates: the deferred pixels of the strip, one per
+  // thread: exact chain, tap from global memory, overwrite (the barrier orders this store after
+  // the provisional one of the tile loop)
+  if constexpr (NEAR && !EXACT) {
+    __syncthreads();
+    const int n = min(tie_count, kL2TieCap);
+    for (int i = tid; i < n; i += kL2Warps * 32) {
+      const unsigned e = tie_list[i];
+      if (e == 0xffffu) continue;
+      const int yy = tile_y0 + (int)((e >> 5) & 15u);
+      const int xx = strip_x0 + (int)(e >> 9) * kL2TileW + (int)(e & 31u);
+      RowCtx<XF> rcx;
+      row_setup<XF>(p, b, yy, rcx);
+      float uj, ui;
+      coords<XF, false>(p, rcx, b, xx, yy, cell, xx - cell * p.w_face, uj, ui);
+      const int xi = __float2int_rn(to_index(ui, p.inv_wm1, p.swm1f));
+      const int yi = __float2int_rn(to_index(uj, p.inv_hm1, p.shm1f));
+      T* d = dst_b + (long long)yy * p.dsh + xx;
+      if (XF == EQB_EQUI2CUBE)
+        d = dst_b + (long long)yy * p.dsh + p.cell_off[cell] + (xx - cell * p.w_face);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const T o = __ldg(src_b + (long long)c * p.ssc + (yi * ssh + xi));
+        Pack<T, 1>::st(d + c * p.dsc, &o);
+      }
     }
   }
 }

@@ -92,9 +92,16 @@ def run(src, rots, z_down, mode, height=None, width=None, clip_output=True,
     mats = _prep.mats_for("rot", rots, z_down, dev)
     tab_x, tab_y = _prep.equirect_tables(height, width, dev)
     clip = K.clip_tensor(src, mode, clip_output, opt.exact_clip, group=opt.clip_group)
+    flags = K.flags_of(src.dtype, opt)
+    if (mode == "nearest" and opt.fast_coords is None
+            and all(r["roll"] == 0 and r["pitch"] == 0 for r in rots)):
+        # identity / pure yaw: every row coordinate is y + 0.5, a rounding tie on every pixel --
+        # interpolated coordinates could decide none of them (the kernel would notice per tile
+        # and take its slower general path): ask for the exact chain up front
+        flags = (flags | _lib.FLAG_EXACT_COORDS) & ~_lib.FLAG_FAST_COORDS
     return K.remap_new(
         src, (bs, c, height, width), allow_channels_last=mode == "bilinear",
-        transform=_lib.EQUI2EQUI, mode=mode, flags=K.flags_of(src.dtype, opt),
+        transform=_lib.EQUI2EQUI, mode=mode, flags=flags,
         batch=bs, channels=c, src_hw=(h_equi, w_equi), dst_hw=(height, width),
         mats=mats, tab_x=tab_x, tab_y=tab_y, clip=clip,
     )

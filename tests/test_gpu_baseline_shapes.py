@@ -309,3 +309,45 @@ def test_static_remap_4k_vs_oracle(dtype, compact):
            identical=float((dp == 0).float().mean()),
            within_tol=float((dp <= tol).float().mean()))
     assert float((dp <= tol).float().mean()) >= 0.9999
+
+
+# ---------------------------------------------------------------------------------------
+# (f) nearest at 4K from interpolated coordinates + tie guard: identical to the exact chain
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "uint8"])
+def test_nearest_4k_tie_guard_equals_the_exact_chain(dtype):
+    """8/16-bit nearest on large launches rounds INTERPOLATED coordinates and re-evaluates the
+    exact chain for every pixel within 4e-3 px of a rounding tie (remap_lean2.cuh).  On a noise
+    image at the headline size -- where the interpolation error is largest (1.7e-3 px) -- the
+    result must equal the exact chain's on every pixel, and with it the oracle's wherever the
+    coordinate is no tie."""
+    rots = cases.bench_rotations(32)
+    rots = [rots[7], rots[19], {"roll": 0.1, "pitch": math.pi / 2 - 0.02, "yaw": 1.0},
+            {"roll": 2.1, "pitch": -1.0, "yaw": -2.0}]
+    img = torch.from_numpy(cases.noise_image((len(rots), 3, 2048, 4096),
+                                             "uint8" if dtype == "uint8" else "float32", 21))
+    x = img.to(DEV) if dtype == "uint8" else img.to(DEV).to(torch.bfloat16)
+    out = equilib_b200.equi2equi(x, rots, mode="nearest")
+    exact = equilib_b200.equi2equi(x, rots, mode="nearest", fast_coords=False)
+    same = float((out == exact).float().mean())
+    record(f"nearest_4k_tie_guard_{dtype}", identical_to_exact_chain=same)
+    assert torch.equal(out, exact), f"{int((out != exact).sum())} elements differ"
+    pers = equilib_b200.equi2pers(x, rots, 1024, 1024, 90.0, mode="nearest")
+    pers_exact = equilib_b200.equi2pers(x, rots, 1024, 1024, 90.0, mode="nearest",
+                                        fast_coords=False)
+    assert torch.equal(pers, pers_exact)
+    ref = oracle.equi2equi(x[:1].cpu(), rots[:1], mode="nearest", flavour="cuda")
+    assert float((out[:1].cpu() == ref).float().mean()) >= 0.9995
+    if dtype == "uint8":
+        # an 8K source: an fp32 coordinate resolves 1e-3 px there, the guard scales with it
+        big = torch.from_numpy(cases.noise_image((1, 3, 4096, 8192), "uint8", 22)).to(DEV)
+        for r in (rots[1], rots[3]):
+            a = equilib_b200.equi2equi(big, [r], mode="nearest")
+            e = equilib_b200.equi2equi(big, [r], mode="nearest", fast_coords=False)
+            assert torch.equal(a, e), f"8K: {int((a != e).sum())} elements differ"
+            a = equilib_b200.equi2pers(big, [r], 1080, 1920, 90.0, mode="nearest")
+            e = equilib_b200.equi2pers(big, [r], 1080, 1920, 90.0, mode="nearest",
+                                       fast_coords=False)
+            assert torch.equal(a, e)

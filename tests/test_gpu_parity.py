@@ -1093,3 +1093,50 @@ def test_lean2_pers2equi_and_small_sources_equal_the_direct_kernel(dtype, monkey
     direct = run_all()
     for i, (a, b) in enumerate(zip(lean2, direct)):
         assert torch.equal(a, b), f"output {i}: {int((a != b).sum())} elements differ"
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16", "uint8"])
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_lean2_nearest_equals_the_direct_kernel(dtype, channels, monkeypatch):
+    """Large nearest launches of equi2equi / equi2pers / equi2cube take the strip-node kernel
+    (one tap per channel from the TMA box, the exact chain on every pixel: the tap is a rounding
+    decision).  Output elements are source elements, so the result must equal the direct-gather
+    kernel's bit for bit -- noise image, poles, seam, ragged sizes, NaN-free."""
+    img = torch.from_numpy(cases.noise_image((2, channels, 512, 1024),
+                                             "uint8" if dtype == "uint8" else "float32", 13))
+    img = img.to(DEV)
+    if dtype not in ("uint8", "float32"):
+        img = img.to(getattr(torch, dtype))
+    rots = [{"roll": 0.3, "pitch": -0.4, "yaw": 1.1}, {"roll": 1.5, "pitch": 1.2, "yaw": -2.9}]
+
+    def run_all():
+        kw = dict(mode="nearest")
+        return [
+            equilib_b200.equi2equi(img, rots, **kw),
+            equilib_b200.equi2equi(img, rots, height=500, width=1002, **kw),
+            equilib_b200.equi2pers(img, rots, 480, 640, 100.0, **kw),
+            equilib_b200.equi2cube(img, rots, 256, "dice", **kw),
+            equilib_b200.equi2cube(img, rots, 192, "horizon", **kw),
+        ]
+
+    lean2 = run_all()
+    monkeypatch.setenv("EQUILIB_B200_NO_STAGE", "1")
+    direct = run_all()
+    for i, (a, b) in enumerate(zip(lean2, direct)):
+        assert torch.equal(a, b), f"output {i}: {int((a != b).sum())} elements differ"
+
+
+def test_lean2_nearest_on_rounding_ties():
+    """Identity and pure-yaw views put every row coordinate on a rounding tie (y + 0.5): the
+    tie guard must hand ALL those pixels to the exact chain -- per tile inside a mixed batch
+    (header flag), up front when the whole batch is pure yaw (host) -- and the result must
+    still equal the direct kernel's."""
+    img = torch.from_numpy(cases.noise_image((3, 3, 512, 1024), "uint8", 17)).to(DEV)
+    mixed = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.0}, {"roll": 0.0, "pitch": 0.0, "yaw": 0.7},
+             {"roll": 0.2, "pitch": -0.3, "yaw": 1.0}]
+    yaw = [{"roll": 0.0, "pitch": 0.0, "yaw": 0.3 * i} for i in range(3)]
+    for x in (img, img.to(torch.bfloat16)):
+        for rots in (mixed, yaw):
+            out = equilib_b200.equi2equi(x, rots, mode="nearest")
+            exact = equilib_b200.equi2equi(x, rots, mode="nearest", fast_coords=False)
+            assert torch.equal(out, exact), f"{int((out != exact).sum())} elements differ"

@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """A/B timing of what the second half of round 2 added (CUDA events, one GPU):
 
-* bicubic through the strip-node kernel (remap_lean2_kernel<..., BICUBIC>) against the generic
-  staged kernel it replaces (EQUILIB_B200_NO_LEAN2=1), headline shapes + config 4 equi2pers;
+* bicubic and nearest through the strip-node kernel (remap_lean2_kernel<..., BICUBIC / NEAREST>)
+  against the kernels they replace (EQUILIB_B200_NO_LEAN2=1: generic staged / direct), headline
+  shapes + config 4 equi2pers;
 * the fused equi -> cube -> equi chain (eqb_equi2cube2equi) against the two launches it
   replaces, config 3 shapes.
 
@@ -59,7 +60,7 @@ def ab(name, fn, out_px, alg_bytes, **kw):
     os.environ.pop("EQUILIB_B200_NO_LEAN2", None)
     report(name + " [strip-node kernel]", timed(fn), out_px, alg_bytes, **kw)
     os.environ["EQUILIB_B200_NO_LEAN2"] = "1"
-    report(name + " [generic staged kernel, EQUILIB_B200_NO_LEAN2=1]", timed(fn), out_px,
+    report(name + " [previous kernel, EQUILIB_B200_NO_LEAN2=1]", timed(fn), out_px,
            alg_bytes, **kw)
     os.environ.pop("EQUILIB_B200_NO_LEAN2", None)
 
@@ -77,6 +78,13 @@ def main():
         ab(name + " clip_output=False",
            lambda: equilib_b200.equi2equi(x, r, mode="bicubic", clip_output=False), b * h * w,
            2 * x.numel() * es)
+        nname = f"2: equi2equi nearest {str(dtype)[6:]} {b}x3x{h}x{w}"
+        ab(nname, lambda: equilib_b200.equi2equi(x, r, mode="nearest"), b * h * w,
+           2 * x.numel() * es)
+        if dtype != torch.float32:
+            report(nname + " fast_coords=False [strip-node kernel, exact chain]",
+                   timed(lambda: equilib_b200.equi2equi(x, r, mode="nearest", fast_coords=False)),
+                   b * h * w, 2 * x.numel() * es)
         if dtype != torch.float16:
             ab(name + " fast_coords=True clip_output=False",
                lambda: equilib_b200.equi2equi(x, r, mode="bicubic", clip_output=False,
