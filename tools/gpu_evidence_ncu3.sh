@@ -1,6 +1,6 @@
 #!/bin/bash
-# ncu --set full capture of the pers2equi strip-node kernel (config 4)
+# ncu captures, call 3 of 4: the uint8 headline kernel (round-1 lean kernel)
 mkdir -p gpurun_out/ev
 O=gpurun_out/ev
-python bench.py --workload p2e_8k_u8_bicubic_b8 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/p2e_plain.json 2>&1 && ncu --set full --import-source on --clock-control none -k regex:remap_lean2 -s 3 -c 1 -o $O/prof_p2e -f python bench.py --workload p2e_8k_u8_bicubic_b8 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_p2e.log 2>&1
+DTYPE=u8 N=3 python tools/prof_one.py >> $O/prof_plain.log 2>&1 && DTYPE=u8 ncu --set full --import-source on --clock-control none -k regex:remap_lean -s 2 -c 1 -o $O/prof_u8 -f python tools/prof_one.py > $O/ncu_u8.log 2>&1
 ls -la $O
