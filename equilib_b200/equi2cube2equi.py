@@ -18,12 +18,13 @@ clamp (for these modes ``clip_output`` cannot change a stored value beyond 2 ulp
 ``_common.clip_tensor``; ``exact_clip=True`` and bicubic always take the two launches).
 
 ``fused=None`` (default) picks by measurement (16 x 4K frames, w_face 1024, B200,
-profiles/r02_round2b.jsonl): **nearest** runs fused -- one chain and one gather per output
-pixel, no cubemap: 1.43 ms instead of 2.00 (fp32), 1.44 instead of 1.86 (bf16), 1.48 / 1.47
-(uint8) -- while **bilinear** runs the two launches: fused, every output pixel evaluates four
-cube pixels of four source taps each (48 gathers per pixel for RGB instead of 12 + 12 staged
-ones), 5.5 ms against 2.5 (fp32) / 1.8 (bf16).  ``fused=True`` forces the single launch (no
-intermediate: 2.4 GB less memory for 16 fp32 frames), ``fused=False`` the two launches.
+profiles/r02_round2b.jsonl): **nearest on 16/32-bit images** runs fused -- one chain and one
+gather per output pixel, no cubemap: 1.43 ms instead of 2.02 (fp32), 1.44 instead of 1.66
+(bf16) -- while uint8 nearest (1.48 fused, 1.37 - 1.54 as two launches) and **bilinear** run the
+two launches: fused, every bilinear output pixel evaluates four cube pixels of four source taps
+each (48 gathers per pixel for RGB instead of 12 + 12 staged ones), 5.5 ms against 2.5 (fp32) /
+1.8 (bf16).  ``fused=True`` forces the single launch (no intermediate: 2.4 GB less memory for
+16 fp32 frames), ``fused=False`` the two launches.
 """
 
 from __future__ import annotations
@@ -98,7 +99,7 @@ def equi2cube2equi(
     # cube2equi's size rule (equilib/cube2equi/base.py:94)
     assert height % 8 == 0 and width % 8 == 0, "ERR: height and width must be multiples of 8"
     if fused is None:
-        fused = mode == "nearest"
+        fused = mode == "nearest" and equi.dtype != torch.uint8
     if fused and fused_ok(equi, mode, clip_output, opt):
         out = run(equi, rots, int(w_face), int(height), int(width), z_down, mode, opt)
     else:

@@ -1036,7 +1036,8 @@ def test_fused_cube_chain_equals_two_launches(dtype, mode):
                                   fast_coords=False)
     two = equilib_b200.cube2equi(cube, "horizon", 128, 256, mode=mode)
     assert torch.equal(obj(img, rots, fused=True), two)
-    # fused=None: nearest fused, bilinear through the two launches (default coordinates)
+    # fused=None: nearest fused (16/32-bit) or two launches, bilinear two launches with the
+    # default coordinates -- nearest is exact either way
     auto = obj(img, rots)
     if mode == "nearest" or dtype == "float32":
         assert torch.equal(auto, two)
