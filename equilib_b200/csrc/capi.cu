@@ -448,8 +448,9 @@ static void setup_tma_nhwc(const eqb_remap_desc* d, Params& p) {
 // The strip-node kernel (remap_lean2.cuh): planar 1 / 3 / 4 channels, equi2equi / equi2pers /
 // equi2cube, TMA.  Bilinear without a clamp: fp32 images run it with the exact chain on every
 // pixel unless EQB_FLAG_FAST_COORDS is set; 8/16-bit images interpolate between the strip's
-// nodes unless EQB_FLAG_EXACT_COORDS is set.  Bicubic (with or without a clamp): the same
-// coordinate policy, every dtype including uint8.
+// nodes unless EQB_FLAG_EXACT_COORDS is set.  Bicubic (with or without a clamp) and nearest: the
+// same coordinate policy, every dtype including uint8 (nearest rounds interpolated coordinates
+// only away from rounding ties: its taps are those of the exact chain either way).
 static bool can_lean2(const eqb_remap_desc* d) {
   if (d->flags & (EQB_FLAG_NO_STAGE | EQB_FLAG_NO_TMA | EQB_FLAG_NO_LEAN | EQB_FLAG_NO_LEAN2 |
                   EQB_FLAG_CHANNELS_LAST))

@@ -1,5 +1,12 @@
-// remap_lean2_kernel: the round-2 headline kernel -- bilinear, TMA-staged, planar 1 / 3 / 4
-// channels, equi2equi / equi2pers / equi2cube.  Designed from ncu captures of its predecessors
+// remap_lean2_kernel<XF, T, NC, EXACT, MODE>: the strip-node kernel -- TMA-staged, planar
+// 1 / 3 / 4 channels.  Round 2 built it for the headline case (bilinear equi2equi / equi2pers /
+// equi2cube); since then it also serves
+//   MODE = BICUBIC   4 x 4 taps from the same boxes, packed row dot-products, in-kernel clamp;
+//                    also pers2equi (fill strips decided from tile corners) and cube2equi from a
+//                    horizon strip;
+//   MODE = NEAREST   one tap per channel; 8/16-bit images round interpolated coordinates away
+//                    from rounding ties and defer the rest to the exact chain (identical taps).
+// Designed from ncu captures of its predecessors
 // (profiles/r01_ncu_remap_bf16_v6_lean_final.txt: 147 instructions per pixel, L1 data pipe
 // 82 %, 2.3 wavefronts per 2-byte tap; profiles/r02_ncu_lean2_v1.txt: 5.3x the source bytes
 // fetched as TMA boxes, a fifth of all issued instructions spinning on the box barrier):
@@ -17,24 +24,27 @@
 //     (origin, shape) and to flags -- smooth (4th and 2nd differences of the nodes small: the
 //     interpolation error is below 1e-3 px and no pixel leaves the node hull by more than
 //     1/4 px, so no per-pixel "inside the box" test is needed), border (a clamp, the wrap or
-//     the footprint shift at the last column could trigger), seam.  Smooth interior tiles
-//     with a box take a straight-line fast path: no reductions, votes, clamps or wraps.
+//     the footprint shift at the last column could trigger; bicubic: a tap would be
+//     reflected), seam, fill (pers2equi), ties (nearest).  Smooth interior tiles with a box
+//     take a straight-line fast path: no reductions, votes, clamps or wraps.
 //  3. SQUARER TILES, TWO BOX BUFFERS.  A 32 x 16 tile of a view rolled by 0.3 rad needs a
 //     48 x 30 box where the 64 x 8 tile of round 1 needed 96 x 40: less than half the L2 ->
 //     shared traffic per pixel.  The box of the NEXT tile is requested while the current one
 //     is blended (two buffers, full / empty mbarriers per buffer, no __syncthreads in the tile
-//     loop, waits back off with nanosleep instead of spinning on the issue slots).
+//     loop, waits suspend in hardware instead of spinning on the issue slots).
 //  4. ALIGNED-WORD TAPS.  The 16 lanes of a row read 16 ADJACENT source pixels per tap
 //     instruction.  A 1- or 2-byte tap is fetched as the aligned 32-bit word that holds it
 //     (lanes sharing a word read the same address: a broadcast, one wavefront) and moved
 //     into place by one PRMT with a per-pixel selector -- the same two instructions as
 //     LDS.U16 + shift, without the extra wavefronts of sub-word accesses (measured: 1.7 per
-//     LDS.U16 when neighbouring lanes read the two halves of one word).
+//     LDS.U16 when neighbouring lanes read the two halves of one word).  A bicubic tap row is
+//     the two or three aligned words that hold its four taps plus funnel shifts.
 //
 // Tiles that are not smooth (source poles), border / seam / ragged tiles and the EXACT variant
 // evaluate the exact chain on every pixel; tiles whose footprint fits no box (poles, seam)
 // gather from global memory -- same values on every path
-// (tests: test_staged_and_direct_kernels_agree).
+// (tests: test_staged_and_direct_kernels_agree, test_lean2_bicubic_equals_the_direct_kernel,
+// test_lean2_nearest_equals_the_direct_kernel).
 #pragma once
 
 #include "remap_kernels.cuh"

@@ -74,7 +74,10 @@ typedef enum eqb_dtype { EQB_U8 = 0, EQB_F16 = 1, EQB_BF16 = 2, EQB_F32 = 3 } eq
                                     4th / 8th pixel of a row + cubic interpolation along  \
                                     x -- measured <= 1.7e-3 px (mean 1.8e-4 px) from the   \
                                     exact chain at 2048 x 4096, test bound 3e-3 px;        \
-                                    DESIGN.md 4.3                                          */
+                                    DESIGN.md 4.3.  Nearest: interpolated coordinates are  \
+                                    rounded only away from rounding ties, every other      \
+                                    pixel gets the exact chain -- identical taps with or   \
+                                    without this flag                     */
 #define EQB_FLAG_FAST_COORDS 32u  /* fp32 images: opt in to the interpolated coordinates  */
 #define EQB_FLAG_FORCE_STAGE 128u /* experiments: staged kernel wherever it is legal           */
 #define EQB_FLAG_NO_TMA 64u       /* staged kernel: cp.async row chunks instead of TMA     */
