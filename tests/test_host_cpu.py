@@ -192,3 +192,59 @@ def test_backend_native_is_an_alias_and_pure_is_rejected():
         assert kw == {}
     with pytest.raises(ValueError):
         _common.check_backend({"backend": "pure"})
+
+
+def test_fused_cube_chain_entry_point_validates_without_gpu():
+    """eqb_equi2cube2equi takes the two descriptors of the launches it replaces and rejects
+    anything else on the host, before any launch; the Python entry has no CPU path either."""
+    L = _lib.lib()
+    a, b = _lib.RemapDesc(), _lib.RemapDesc()
+    assert L.eqb_equi2cube2equi(None, None, None) == -1
+    assert L.eqb_equi2cube2equi(ctypes.byref(a), ctypes.byref(b), None) == -1
+    assert b"EQUI2CUBE followed by CUBE2EQUI" in L.eqb_last_error()
+    for d in (a, b):
+        d.mode, d.dtype, d.batch, d.channels = 1, _lib.F32, 2, 3
+        d.w_face, d.n_cells = 16, 6
+        d.mats = d.tab_x = d.tab_y = d.itab_x = 16  # non-null, never dereferenced on the host
+    a.transform, a.src_h, a.src_w, a.dst_h, a.dst_w = _lib.EQUI2CUBE, 64, 128, 16, 96
+    b.transform, b.src_h, b.src_w, b.dst_h, b.dst_w = _lib.CUBE2EQUI, 16, 96, 64, 128
+    a.src, a.src_stride_b, a.src_stride_c, a.src_stride_h = 16, 3 * 64 * 128, 64 * 128, 128
+    b.mode = 2  # bicubic on one side only
+    assert L.eqb_equi2cube2equi(ctypes.byref(a), ctypes.byref(b), None) == -1
+    assert b"differ" in L.eqb_last_error()
+    a.mode = 2
+    assert L.eqb_equi2cube2equi(ctypes.byref(a), ctypes.byref(b), None) == -2
+    assert b"nearest and bilinear" in L.eqb_last_error()
+    a.mode = b.mode = 1
+    assert L.eqb_equi2cube2equi(ctypes.byref(a), ctypes.byref(b), None) == -1  # dst is null
+    assert b"null" in L.eqb_last_error()
+    assert hasattr(equilib_b200, "Equi2Cube2Equi") and hasattr(equilib_b200, "equi2cube2equi")
+    with pytest.raises(ValueError, match="no CPU path"):
+        equilib_b200.equi2cube2equi(torch.zeros(3, 8, 16), ROT, 4, 8, 16)
+
+
+def test_environment_switches_follow_os_environ(monkeypatch):
+    """flags_of reads the EQUILIB_B200_* switches from the bytes map behind os.environ (a
+    launch's host path must not pay ten os.environ.get calls): it has to see what
+    monkeypatch / os.environ assignments do, immediately."""
+    from equilib_b200 import _common as K
+
+    opt = K.Options()
+    base = K.flags_of(torch.uint8, opt)
+    assert base == 0
+    monkeypatch.setenv("EQUILIB_B200_NO_TMA", "1")
+    assert K.flags_of(torch.uint8, opt) == _lib.FLAG_NO_TMA
+    monkeypatch.setenv("EQUILIB_B200_NO_LEAN2", "1")
+    monkeypatch.setenv("EQUILIB_B200_FAST_COORDS", "0")
+    assert K.flags_of(torch.uint8, opt) == (_lib.FLAG_NO_TMA | _lib.FLAG_NO_LEAN2
+                                            | _lib.FLAG_EXACT_COORDS)
+    monkeypatch.delenv("EQUILIB_B200_NO_TMA")
+    monkeypatch.delenv("EQUILIB_B200_NO_LEAN2")
+    monkeypatch.setenv("EQUILIB_B200_FAST_COORDS", "1")
+    assert K.flags_of(torch.float32, opt) == _lib.FLAG_FAST_COORDS
+    assert K.flags_of(torch.float32, K.Options(fast_coords=False)) == _lib.FLAG_EXACT_COORDS
+    monkeypatch.delenv("EQUILIB_B200_FAST_COORDS")
+    monkeypatch.setenv("EQUILIB_B200_WARP_SHAPE", "2")
+    assert K.flags_of(torch.uint8, opt) == 2 << _lib.FLAG_WARP_SHAPE_SHIFT
+    monkeypatch.delenv("EQUILIB_B200_WARP_SHAPE")
+    assert K.flags_of(torch.uint8, K.Options(saturate_uint8=True)) == _lib.FLAG_SATURATE_U8
