@@ -25,6 +25,7 @@ NCU = {  # report -> (summary file, traffic.json key)
     "prof_u8.ncu-rep": ("r02_ncu_lean_u8_headline.txt", "e2e_4k_u8_b32"),
     "prof_bicubic.ncu-rep": ("r02_ncu_lean2_bicubic_bf16.txt", None),
     "prof_p2e.ncu-rep": ("r02_ncu_lean2_pers2equi_u8_bicubic.txt", "p2e_8k_u8_bicubic_b8"),
+    "prof_nearest.ncu-rep": ("r02_ncu_lean2_nearest_bf16.txt", None),
 }
 COPY = {  # gpurun_out/ev file -> profiles file
     "pytest_gpu.log": "r02_pytest_gpu.log",
