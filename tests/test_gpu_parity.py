@@ -992,11 +992,11 @@ def test_lean2_bicubic_interpolated_coordinates_vs_oracle(dtype):
     if dtype == "uint8":
         d = np.abs(out.cpu().numpy().astype(int) - ref.numpy().astype(int))
         d = np.minimum(d, 256 - d)
-        assert np.mean(d <= 1) >= 0.9995 and rate(np.mean(d == 0), 0.98)
+        assert np.mean(d <= 1) >= 0.9995 and rate(np.mean(d == 0), 0.998)  # measured 0.99978
     elif dtype == "bfloat16":
         o, r = out.float().cpu().numpy(), ref.float().numpy()
         assert close_except_seam(o, r, 2.0 ** -7, 0.9995)
-        assert rate(np.mean(o == r), 0.98)
+        assert rate(np.mean(o == r), 0.998)  # measured 0.99951
     else:
         assert close_except_seam(out.cpu().numpy(), ref.numpy(), 2e-3, 0.9995)
 
